@@ -1,0 +1,170 @@
+/*
+ * topo4d_b200.h -- C ABI of libtopo4d_b200.so (sm_100a).
+ *
+ * The drop-in boundary for Topo4D's two native hot paths.  Plain pointers and sizes only:
+ * no torch / numpy / C++ types.  The caller owns every byte of memory (device or host as
+ * stated); the library never allocates device memory and keeps no global mutable state, so
+ * one process per GPU (torchrun) and one thread per GPU are both safe.  All entry points
+ * enqueue on the given CUDA stream and return 0, or a negative GS_E_* / F3D_E_* code
+ * (never throw); `*_last_error()` returns a static description of a code.
+ *
+ * What each entry point replaces in the reference:
+ *   gs_forward / gs_backward ... `_C.rasterize_gaussians[_backward]` of the un-vendored
+ *       `diff_gaussian_rasterization` extension that `GaussianRasterizer.forward/backward`
+ *       dispatch to; reference call sites train.py:307,388,463,484 (render),
+ *       train.py:667,738 (loss.backward()), settings built at helpers.py:73-86,
+ *       inputs built at helpers.py:91-112.
+ *   gs_mark_visible ........... `_C.mark_visible` behind `GaussianRasterizer.markVisible`
+ *       (API completeness; Topo4D never calls it).
+ *   f3d_render_colors[_host] .. `_render_colors_core` (face3d/mesh/cython/mesh_core.cpp:169-234)
+ *       as bound by `render_colors_core` (face3d/mesh/cython/mesh_core_cython.pyx:64-77) and
+ *       reached through face3d/mesh/render.py:52-86 from helpers.py:956.
+ */
+#ifndef TOPO4D_B200_H_
+#define TOPO4D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gs_stream_t;          /* a cudaStream_t */
+
+/* ---- error codes ---- */
+#define GS_OK                 0
+#define GS_E_BAD_ARGS        -1     /* NULL / inconsistent arguments (both or neither of shs|colors, ...) */
+#define GS_E_WORKSPACE_SMALL -2     /* workspace_bytes < gs_workspace_bytes(...) */
+#define GS_E_CUDA            -3     /* a CUDA runtime call failed; see gs_last_cuda_error() */
+#define GS_E_OVERFLOW        -4     /* (only from gs_read_status) instances needed > cap_instances */
+#define GS_E_UNSUPPORTED     -5
+
+/* ---- per-view camera block: GS_CAM_FLOATS consecutive floats on the DEVICE per view ----
+ * Mirrors GaussianRasterizationSettings (helpers.py:73-86).  Matrices are the 16 consecutive
+ * floats the reference passes: element [4*col+row] of the mathematical matrix
+ * (viewmatrix = w2c^T, projmatrix = (P w2c)^T in PyTorch row-major terms). */
+#define GS_CAM_FLOATS   48
+#define GS_CAM_VIEW      0          /* [16] viewmatrix   */
+#define GS_CAM_PROJ     16          /* [16] projmatrix   */
+#define GS_CAM_CAMPOS   32          /* [3]  campos       */
+#define GS_CAM_BG       35          /* [3]  bg           */
+#define GS_CAM_TANFOVX  38
+#define GS_CAM_TANFOVY  39          /* 40..47 reserved, must be 0 */
+
+/* ---- problem description shared by forward and backward ---- */
+typedef struct GsProblem {
+    int32_t N;                      /* Gaussians                                              */
+    int32_t V;                      /* camera views rendered by this call (the reference: 1)  */
+    int32_t H, W;                   /* image size, shared by all V views                      */
+    int32_t sh_degree;              /* active SH degree 0..3 (settings.sh_degree)             */
+    int32_t sh_coeffs;              /* M: coefficients stored per Gaussian in `shs` [N,M,3]   */
+    float   scale_modifier;
+    int32_t debug;                  /* !=0: synchronise + check after every stage             */
+    int64_t cap_instances;          /* capacity (tile,Gaussian) instances of the workspace    */
+    /* inputs, DEVICE pointers, fp32, contiguous.  Exactly one of shs|colors_precomp and
+       exactly one of (scales,rotations)|cov3D_precomp must be non-NULL. */
+    const float* means3D;           /* [N,3] */
+    const float* shs;               /* [N,M,3] */
+    const float* colors_precomp;    /* [N,3]   */
+    const float* opacities;         /* [N] (the reference passes [N,1]) */
+    const float* scales;            /* [N,3]   */
+    const float* rotations;         /* [N,4] (w,x,y,z), used as given (not renormalised) */
+    const float* cov3D_precomp;     /* [N,6]   */
+    const float* cameras;           /* [V,GS_CAM_FLOATS] */
+    /* state kept between forward and backward, DEVICE, caller-owned */
+    void*   workspace;
+    size_t  workspace_bytes;
+} GsProblem;
+
+typedef struct GsForwardOut {       /* DEVICE pointers */
+    float*   color;                 /* [V,3,H,W] */
+    float*   depth;                 /* [V,1,H,W] un-normalised sum(alpha_i T_i z_i), no bg */
+    float*   alpha;                 /* [V,1,H,W] sum(alpha_i T_i) */
+    int32_t* radii;                 /* [V,N] screen radius in px, 0 = culled */
+} GsForwardOut;
+
+typedef struct GsBackwardIO {       /* DEVICE pointers */
+    const float* dL_dcolor;         /* [V,3,H,W] */
+    const float* dL_ddepth;         /* [V,1,H,W] or NULL (= zeros) */
+    const float* dL_dalpha;         /* [V,1,H,W] or NULL (= zeros) */
+    const int32_t* radii;           /* [V,N] as returned by forward */
+    /* outputs: OVERWRITTEN with the sum over the V views (never accumulated into). */
+    float* dL_dmeans3D;             /* [N,3] */
+    float* dL_dmeans2D;             /* [N,3] NDC-scaled screen-space gradient, z = 0 */
+    float* dL_dshs;                 /* [N,M,3]  (when shs given)            */
+    float* dL_dcolors;              /* [N,3]    (when colors_precomp given) */
+    float* dL_dopacities;           /* [N]   */
+    float* dL_dscales;              /* [N,3] (when scales/rotations given)  */
+    float* dL_drotations;           /* [N,4] */
+    float* dL_dcov3D;               /* [N,6] (when cov3D_precomp given)     */
+} GsBackwardIO;
+
+typedef struct GsStatus {           /* host copy of the device status block */
+    int64_t num_instances;          /* `num_rendered`: instances the V views need            */
+    int64_t cap_instances;
+    int32_t overflow;               /* 1 if num_instances > cap_instances (outputs invalid)  */
+    int32_t max_tile_instances;     /* longest per-tile list                                 */
+} GsStatus;
+
+/* Byte size of the workspace for (N, V, H, W, cap_instances).  Pure host arithmetic. */
+size_t gs_workspace_bytes(int32_t N, int32_t V, int32_t H, int32_t W, int64_t cap_instances);
+
+/* Forward for V views: preprocess -> tile-bin -> per-tile depth sort + record gather ->
+ * front-to-back blend.  Asynchronous.  Fills the device status block inside the workspace. */
+int gs_forward(const GsProblem* p, const GsForwardOut* out, gs_stream_t stream);
+
+/* Backward for the same V views; needs the workspace exactly as forward left it. */
+int gs_backward(const GsProblem* p, const GsBackwardIO* io, gs_stream_t stream);
+
+/* Copies the status block to the host (synchronises `stream`).  Returns GS_E_OVERFLOW if the
+ * last forward needed more instances than the workspace holds (grow cap_instances, retry). */
+int gs_read_status(const GsProblem* p, GsStatus* status_host, gs_stream_t stream);
+
+/* Runs only preprocess + tile count + scan and returns the exact instance count (synchronises).
+ * Lets a caller size `cap_instances` before the first real forward. */
+int gs_count_instances(const GsProblem* p, int64_t* num_instances_host, gs_stream_t stream);
+
+/* visible[i] = view-space z of means3D[i] > 0.2 for camera block `camera` (one view). */
+int gs_mark_visible(int32_t N, const float* means3D, const float* camera, uint8_t* visible, gs_stream_t stream);
+
+/* Introspection for the bit-exact index tests: device pointers into the workspace. */
+typedef struct GsWorkspaceView {
+    const uint32_t* tile_start;     /* [V*tiles+1] exclusive scan: tile t of view v owns [start[v*tiles+t], start[..+1]) */
+    const uint32_t* sorted_ids;     /* [cap] Gaussian index per instance, tile-major, (depth, index) ascending */
+    const float*    sorted_records; /* [cap,12] 48-byte records (x,y,conA,conB | conC,opacity,depth,id | r,g,b,_) */
+    const float*    geom_records;   /* [V*N,12] same layout, per (view, Gaussian) */
+    const float*    final_T;        /* [V,H,W] */
+    const uint32_t* n_contrib;      /* [V,H,W] */
+    const float*    grad2d;         /* [V*N,12] dL/d(pix.x,pix.y,conA,conB) | (conC,opacity,depth,_) | (r,g,b,_) after backward */
+    int32_t tiles_x, tiles_y;
+} GsWorkspaceView;
+int gs_workspace_view(const GsProblem* p, GsWorkspaceView* view);
+
+const char* gs_last_error(int code);
+const char* gs_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * face3d render_colors
+ * Semantics of _render_colors_core (mesh_core.cpp:169-234): painter with strict `>` depth test
+ * (larger z = nearer, first triangle wins ties), integer bbox clipped to the image, the 2-px
+ * border rule, barycentric colour interpolation; `image` [h,w,c] and `depth_buffer` [h,w] are
+ * updated IN PLACE (image keeps its previous content where nothing is drawn).
+ * ---------------------------------------------------------------------------------------- */
+#define F3D_OK            0
+#define F3D_E_BAD_ARGS   -1
+#define F3D_E_CUDA       -3
+#define F3D_E_WORKSPACE  -2
+
+/* Device-pointer path.  workspace: f3d_workspace_bytes(ntri,h,w) bytes of device scratch. */
+size_t f3d_workspace_bytes(int32_t ntri, int32_t h, int32_t w);
+int f3d_render_colors(float* image, const float* vertices, const int32_t* triangles, const float* colors,
+                      float* depth_buffer, int32_t nver, int32_t ntri, int32_t h, int32_t w, int32_t c,
+                      void* workspace, size_t workspace_bytes, gs_stream_t stream);
+/* Optional fused epilogue of helpers.py:959: out_u8[h,w,c] = (uint8)(image*255) (C truncation). */
+int f3d_image_to_u8(const float* image, uint8_t* out_u8, int64_t count, gs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPO4D_B200_H_ */

@@ -1,0 +1,99 @@
+"""ctypes binding of libtopo4d_b200.so (the C ABI in include/topo4d_b200.h).
+
+The product path has no CPU fallback: if the CUDA library is missing and cannot be built,
+importing this module's :func:`lib` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+GS_CAM_FLOATS = 48
+GS_OK, GS_E_BAD_ARGS, GS_E_WORKSPACE_SMALL, GS_E_CUDA, GS_E_OVERFLOW, GS_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+_vp = C.c_void_p
+
+
+class GsProblem(C.Structure):
+    _fields_ = [("N", C.c_int32), ("V", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32), ("scale_modifier", C.c_float),
+                ("debug", C.c_int32), ("cap_instances", C.c_int64),
+                ("means3D", _vp), ("shs", _vp), ("colors_precomp", _vp), ("opacities", _vp), ("scales", _vp),
+                ("rotations", _vp), ("cov3D_precomp", _vp), ("cameras", _vp),
+                ("workspace", _vp), ("workspace_bytes", C.c_size_t)]
+
+
+class GsForwardOut(C.Structure):
+    _fields_ = [("color", _vp), ("depth", _vp), ("alpha", _vp), ("radii", _vp)]
+
+
+class GsBackwardIO(C.Structure):
+    _fields_ = [("dL_dcolor", _vp), ("dL_ddepth", _vp), ("dL_dalpha", _vp), ("radii", _vp),
+                ("dL_dmeans3D", _vp), ("dL_dmeans2D", _vp), ("dL_dshs", _vp), ("dL_dcolors", _vp),
+                ("dL_dopacities", _vp), ("dL_dscales", _vp), ("dL_drotations", _vp), ("dL_dcov3D", _vp)]
+
+
+class GsStatus(C.Structure):
+    _fields_ = [("num_instances", C.c_int64), ("cap_instances", C.c_int64), ("overflow", C.c_int32),
+                ("max_tile_instances", C.c_int32)]
+
+
+class GsWorkspaceView(C.Structure):
+    _fields_ = [("tile_start", _vp), ("sorted_ids", _vp), ("sorted_records", _vp), ("geom_records", _vp),
+                ("final_T", _vp), ("n_contrib", _vp), ("grad2d", _vp), ("tiles_x", C.c_int32), ("tiles_y", C.c_int32)]
+
+
+# every symbol include/topo4d_b200.h declares: (name, restype, argtypes)
+SYMBOLS = {
+    "gs_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "gs_forward": (C.c_int, [C.POINTER(GsProblem), C.POINTER(GsForwardOut), _vp]),
+    "gs_backward": (C.c_int, [C.POINTER(GsProblem), C.POINTER(GsBackwardIO), _vp]),
+    "gs_read_status": (C.c_int, [C.POINTER(GsProblem), C.POINTER(GsStatus), _vp]),
+    "gs_count_instances": (C.c_int, [C.POINTER(GsProblem), C.POINTER(C.c_int64), _vp]),
+    "gs_mark_visible": (C.c_int, [C.c_int32, _vp, _vp, _vp, _vp]),
+    "gs_workspace_view": (C.c_int, [C.POINTER(GsProblem), C.POINTER(GsWorkspaceView)]),
+    "gs_last_error": (C.c_char_p, [C.c_int]),
+    "gs_last_cuda_error": (C.c_char_p, []),
+    "f3d_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "f3d_render_colors": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    _vp, C.c_size_t, _vp]),
+    "f3d_image_to_u8": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+}
+
+_LIB = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def lib():
+    """Load (building in-tree if stale/missing) the CUDA library.  Raises if that is impossible."""
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB_PATH
+        if not os.path.exists(path) or os.environ.get("TOPO4D_B200_REBUILD") == "1":
+            path = _build.build_library()
+        handle = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)        # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+class GsError(RuntimeError):
+    pass
+
+
+def check(code: int, what: str = "") -> None:
+    if code == 0:
+        return
+    L = lib()
+    msg = L.gs_last_error(code).decode()
+    if code == GS_E_CUDA:
+        msg += " -- " + L.gs_last_cuda_error().decode()
+    raise GsError(f"{what}: {msg} (code {code})")

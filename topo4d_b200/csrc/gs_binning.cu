@@ -1,0 +1,199 @@
+// gs_binning.cu -- tile scan (K2) and per-tile depth sort + record gather (K4).
+//
+// Replaces upstream's InclusiveSum + duplicateWithKeys + 64-bit DeviceRadixSort + identifyTileRanges
+// (SURVEY.md 2.2 K2-K5).  Instead of ~7 radix passes over 12-byte pairs in HBM, instances are
+// bucketed by tile with atomics (gs_preprocess.cu), the tile histogram is scanned here (tile
+// ranges fall out directly), and every tile's short list is sorted by (depth_bits, index) inside
+// shared memory by one CTA.  Keys are distinct 64-bit integers, so the result is exactly the order
+// a stable radix sort on (tile | depth_bits) of index-ordered duplicates gives: bit-exact lists.
+// The same CTA then gathers the 48-byte per-Gaussian records into tile order, so both blend passes
+// stream each chunk with one contiguous bulk-async copy.
+#include "gs_common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;   // SCAN_THREADS * SCAN_ITEMS == GS_SCAN_ELEMS_PER_BLOCK
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
+{
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+
+// phase A: per-block totals (also the per-tile maximum for the status block)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const GsParams p)
+{
+    __shared__ uint32_t s_sum[32];
+    __shared__ uint32_t s_max[32];
+    const long long n = p.total_tiles;
+    const long long base = (long long)blockIdx.x * GS_SCAN_ELEMS_PER_BLOCK + threadIdx.x * SCAN_ITEMS;
+    uint32_t sum = 0, mx = 0;
+    #pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const long long e = base + k;
+        const uint32_t c = e < n ? p.tile_count[e] : 0u;
+        sum += c; mx = max(mx, c);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_sum[w] = sum; s_max[w] = mx; }
+    __syncthreads();
+    if (w == 0) {
+        sum = s_sum[lane]; mx = s_max[lane];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) {
+            p.block_sums[blockIdx.x] = sum;
+            atomicMax(&p.status->max_tile_instances, (int)mx);
+        }
+    }
+}
+
+// phase B: exclusive scan of every block's chunk, offset by the sum of the preceding blocks
+__global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const GsParams p)
+{
+    __shared__ unsigned long long s_red[32];
+    __shared__ uint32_t s_warp[32];
+    __shared__ unsigned long long s_prefix;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // prefix of preceding blocks (64-bit so an overflowing total is detected, not wrapped)
+    unsigned long long pre = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += SCAN_THREADS) pre += p.block_sums[b];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+    if (lane == 0) s_red[w] = pre;
+    __syncthreads();
+    if (w == 0) {
+        pre = s_red[lane];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+        if (lane == 0) s_prefix = pre;
+    }
+    __syncthreads();
+    pre = s_prefix;
+
+    const long long n = p.total_tiles;   // tile_start has n+1 entries
+    const long long base = (long long)blockIdx.x * GS_SCAN_ELEMS_PER_BLOCK + threadIdx.x * SCAN_ITEMS;
+    uint32_t c[SCAN_ITEMS], tsum = 0;
+    #pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { const long long e = base + k; c[k] = e < n ? p.tile_count[e] : 0u; tsum += c[k]; }
+    const uint32_t incl = warp_incl_scan(tsum, lane);
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) { uint32_t x = s_warp[lane]; x = warp_incl_scan(x, lane); s_warp[lane] = x; }
+    __syncthreads();
+    unsigned long long run = pre + (w > 0 ? s_warp[w - 1] : 0u) + (incl - tsum);
+    #pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const long long e = base + k;
+        if (e <= n) p.tile_start[e] = (uint32_t)(run > 0xffffffffull ? 0xffffffffull : run);
+        if (e < n) p.tile_fill[e] = 0u;
+        run += c[k];
+    }
+    if (base <= n && n < base + SCAN_ITEMS) {   // the thread that owns element n holds the grand total
+        unsigned long long total = pre + (w > 0 ? s_warp[w - 1] : 0u) + (incl - tsum);
+        for (int k = 0; k < SCAN_ITEMS && base + k < n; k++) total += c[k];
+        p.status->num_instances = total;
+        p.status->cap_instances = (unsigned long long)p.cap;
+        p.status->overflow = total > (unsigned long long)p.cap ? 1 : 0;
+    }
+}
+
+// ---- K4 ----
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_SMEM_KEYS = 4096;   // 32 KB of 64-bit keys; longer lists are sorted in place in global memory
+
+// Bitonic network in the "flip / disperse" form: every compare-exchange moves the smaller key to the
+// lower index, so virtual +inf padding above `n` never moves and arbitrary n needs no real padding.
+template <typename KeyPtr>
+__device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nthreads)
+{
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int k = 2; k <= n2; k <<= 1) {
+        // flip: partner is the mirror position inside the k-block
+        for (int t = tid; t < (n2 >> 1); t += nthreads) {
+            const int blk = t / (k >> 1), off = t % (k >> 1);
+            const int i = blk * k + off, j = blk * k + (k - 1 - off);
+            if (j < n) {
+                const unsigned long long a = keys[i], b = keys[j];
+                if (a > b) { keys[i] = b; keys[j] = a; }
+            }
+        }
+        __syncthreads();
+        for (int jj = k >> 2; jj > 0; jj >>= 1) {
+            for (int t = tid; t < (n2 >> 1); t += nthreads) {
+                const int i = ((t / jj) * (jj << 1)) + (t % jj), j = i + jj;
+                if (j < n) {
+                    const unsigned long long a = keys[i], b = keys[j];
+                    if (a > b) { keys[i] = b; keys[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParams p)
+{
+    __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
+    const int tid = threadIdx.x;
+    for (long long tg = blockIdx.x; tg < p.total_tiles; tg += gridDim.x) {
+        unsigned long long start = p.tile_start[tg], end = p.tile_start[tg + 1];
+        if (end > (unsigned long long)p.cap) end = (unsigned long long)p.cap;
+        if (start >= end) continue;
+        const int n = (int)(end - start);
+        const int v = (int)(tg / p.tiles);
+        unsigned long long* gk = p.pairs + start;
+        const unsigned long long* sorted;
+        if (n <= SORT_SMEM_KEYS) {
+            for (int t = tid; t < n; t += SORT_THREADS) s_keys[t] = gk[t];
+            __syncthreads();
+            if (n > 1) bitonic_sort(s_keys, n, tid, SORT_THREADS);
+            sorted = s_keys;
+        } else {
+            __syncthreads();
+            bitonic_sort(gk, n, tid, SORT_THREADS);     // in place in L2-resident global memory
+            sorted = gk;
+        }
+        // gather: 3 x 16 bytes per record, coalesced writes
+        const float4* __restrict__ geom = p.geom + (size_t)v * p.N * 3;
+        float4* __restrict__ rec = p.sorted_rec + start * 3;
+        for (int t = tid; t < n * 3; t += SORT_THREADS) {
+            const int k = t / 3, part = t - k * 3;
+            const uint32_t id = (uint32_t)(sorted[k] & 0xffffffffull);
+            rec[t] = __ldg(geom + (size_t)id * 3 + part);
+            if (part == 0) p.sorted_ids[start + k] = id;
+        }
+        __syncthreads();   // s_keys is reused by the next tile
+    }
+}
+
+}  // namespace
+
+void gs_launch_tile_scan(const GsParams& p, cudaStream_t s)
+{
+    scan_reduce_kernel<<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
+    scan_write_kernel<<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
+}
+
+void gs_launch_sort_gather(const GsParams& p, int num_sms, cudaStream_t s)
+{
+    long long blocks = p.total_tiles;
+    const long long maxb = (long long)num_sms * 8;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    sort_gather_kernel<<<(unsigned)blocks, SORT_THREADS, 0, s>>>(p);
+}

@@ -1,0 +1,153 @@
+// gs_common.cuh -- shared declarations of the sm_100a Gaussian rasterizer kernels.
+//
+// Data layout in HBM (all caller-owned, carved out of GsProblem.workspace by ws_layout()):
+//   status        GsStatusDev                       device status block
+//   tile_count    u32 [V*T + 1]                     instances per (view, tile)
+//   tile_start    u32 [V*T + 1]                     exclusive scan of tile_count; [V*T] = I
+//   tile_fill     u32 [V*T]                         scatter cursors
+//   block_sums    u32 [scan blocks]                 scan scratch
+//   clamped       u8  [V*N]                         SH clamp bits (r,g,b)
+//   geom          48-byte record [V*N]              (x,y,conA,conB | conC,opacity,depth,id | r,g,b,_)
+//   pairs         u64 [cap]                         (depth_bits<<32 | id), tile-major, unsorted
+//   sorted_ids    u32 [cap]
+//   sorted_rec    48-byte record [cap]              tile-sorted copy of geom: ONE contiguous bulk copy per chunk
+//   final_T       f32 [V*H*W]
+//   n_contrib     u32 [V*H*W]
+//   grad2d        48-byte record [V*N]              (dpix.x,dpix.y,dconA,dconB | dconC,dopacity,ddepth,_ | dr,dg,db,_)
+// T = tiles per view = ceil(W/16)*ceil(H/16).  The binning tile is 16x16 (reference contract).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/topo4d_b200.h"
+
+#define GS_TILE 16
+#define GS_REC_FLOATS 12            // 48-byte records
+#define GS_NEAR_CULL 0.2f
+#define GS_LOWPASS 0.3f
+#define GS_ALPHA_CAP 0.99f
+#define GS_ALPHA_MIN (1.0f / 255.0f)
+#define GS_T_MIN 0.0001f
+
+struct GsStatusDev {
+    unsigned long long num_instances;
+    unsigned long long cap_instances;
+    int overflow;
+    int max_tile_instances;
+    int pad[2];
+};
+
+struct GsLayout {
+    size_t off_status, off_tile_count, off_tile_start, off_tile_fill, off_block_sums, off_clamped, off_geom,
+           off_pairs, off_sorted_ids, off_sorted_rec, off_final_T, off_n_contrib, off_grad2d, total;
+    int tiles_x, tiles_y, tiles;        // per view
+    long long total_tiles;              // V * tiles
+    int scan_blocks;
+};
+
+#define GS_SCAN_ELEMS_PER_BLOCK 4096    // 1024 threads x 4
+
+static inline size_t gs_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static inline GsLayout gs_make_layout(int N, int V, int H, int W, long long cap)
+{
+    GsLayout L;
+    L.tiles_x = (W + GS_TILE - 1) / GS_TILE;
+    L.tiles_y = (H + GS_TILE - 1) / GS_TILE;
+    L.tiles = L.tiles_x * L.tiles_y;
+    L.total_tiles = (long long)V * L.tiles;
+    L.scan_blocks = (int)((L.total_tiles + 1 + GS_SCAN_ELEMS_PER_BLOCK - 1) / GS_SCAN_ELEMS_PER_BLOCK);
+    const size_t A = 256;
+    size_t o = 0;
+    const size_t VN = (size_t)V * (size_t)(N > 0 ? N : 1);
+    const size_t P = (size_t)V * H * W;
+    const size_t C = (size_t)(cap > 0 ? cap : 1);
+    L.off_status = o;      o = gs_align_up(o + sizeof(GsStatusDev), A);
+    L.off_tile_count = o;  o = gs_align_up(o + 4 * (size_t)(L.total_tiles + 1), A);
+    L.off_tile_start = o;  o = gs_align_up(o + 4 * (size_t)(L.total_tiles + 1), A);
+    L.off_tile_fill = o;   o = gs_align_up(o + 4 * (size_t)(L.total_tiles + 1), A);
+    L.off_block_sums = o;  o = gs_align_up(o + 4 * (size_t)(L.scan_blocks + 1), A);
+    L.off_clamped = o;     o = gs_align_up(o + VN, A);
+    L.off_geom = o;        o = gs_align_up(o + 48 * VN, A);
+    L.off_pairs = o;       o = gs_align_up(o + 8 * C, A);
+    L.off_sorted_ids = o;  o = gs_align_up(o + 4 * C, A);
+    L.off_sorted_rec = o;  o = gs_align_up(o + 48 * C, A);
+    L.off_final_T = o;     o = gs_align_up(o + 4 * P, A);
+    L.off_n_contrib = o;   o = gs_align_up(o + 4 * P, A);
+    L.off_grad2d = o;      o = gs_align_up(o + 48 * VN, A);
+    L.total = o;
+    return L;
+}
+
+// Everything a kernel needs, passed by value (__grid_constant__-sized, < 400 bytes).
+struct GsParams {
+    int N, V, H, W, deg, M;
+    int tiles_x, tiles_y, tiles;
+    long long total_tiles;
+    long long cap;
+    float mod;
+    const float *means3D, *shs, *colors, *opac, *scales, *rots, *cov3D, *cams;
+    GsStatusDev* status;
+    uint32_t *tile_count, *tile_start, *tile_fill, *block_sums;
+    uint8_t* clamped;
+    float4* geom;
+    unsigned long long* pairs;
+    uint32_t* sorted_ids;
+    float4* sorted_rec;
+    float* final_T;
+    uint32_t* n_contrib;
+    float4* grad2d;
+    int scan_blocks;
+};
+
+// launchers implemented in the kernel translation units
+void gs_launch_preprocess(const GsParams& p, int32_t* radii, cudaStream_t s);
+void gs_launch_scatter(const GsParams& p, const int32_t* radii, cudaStream_t s);
+void gs_launch_mark_visible(int N, const float* means3D, const float* cam, uint8_t* visible, cudaStream_t s);
+void gs_launch_tile_scan(const GsParams& p, cudaStream_t s);
+void gs_launch_sort_gather(const GsParams& p, int num_sms, cudaStream_t s);
+void gs_launch_blend_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s);
+void gs_launch_blend_bwd(const GsParams& p, const float* g_color, const float* g_depth, const float* g_alpha,
+                         int num_sms, cudaStream_t s);
+void gs_launch_preprocess_bwd(const GsParams& p, const GsBackwardIO& io, cudaStream_t s);
+
+#ifdef __CUDACC__
+// ---- mbarrier + bulk async copy (TMA-family, SASS: UBLKCP / SYNCS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared::cta bulk copy, completion counted in bytes on `bar`.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 16-byte vector reduction to global memory (sm_90+): one RED per 4 floats.
+__device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+#endif

@@ -1,0 +1,227 @@
+// gs_preprocess.cu -- forward preprocess (K1), tile scatter (K3) and markVisible (K10).
+//
+// COMPILED WITH --fmad=false: every expression here is IEEE fp32, left to right, unfused,
+// with IEEE division / sqrtf, so that radius, tile rectangle, depth key -- and therefore every
+// tile/bin index downstream -- are bit-identical to the CPU oracle.
+//
+// Replaces upstream preprocessCUDA / duplicateWithKeys of the un-vendored rasterizer that
+// GaussianRasterizer.forward (reference call sites train.py:307,388) dispatches to.
+// Design differences (B200-first, not a port):
+//   * one launch covers all V views (thread = (view, Gaussian)); per-Gaussian outputs are packed
+//     into ONE 48-byte record written with three 16-byte stores (geom[], layout in gs_common.cuh);
+//   * no per-Gaussian prefix sum: tiles are counted with atomics here, scanned per TILE, and the
+//     per-tile order is restored later by a (depth,index) sort, which is the same total order a
+//     stable (tile|depth) radix sort produces -- so no host sync is needed to size buffers.
+#include "gs_common.cuh"
+
+namespace {
+
+__device__ __constant__ float kC0 = 0.28209479177387814f;
+__device__ __constant__ float kC1 = 0.4886025119029199f;
+__device__ __constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                        -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                        0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                        -0.5900435899266435f};
+
+struct Rect { int minx, miny, maxx, maxy; };
+
+// tile rectangle of a splat: C truncation toward zero, then clamp to the grid (max exclusive)
+__device__ __forceinline__ Rect tile_rect(float pix_x, float pix_y, float radius, int gx, int gy)
+{
+    Rect r;
+    r.minx = (int)((pix_x - radius) / (float)GS_TILE);
+    r.miny = (int)((pix_y - radius) / (float)GS_TILE);
+    r.maxx = (int)((pix_x + radius + (float)(GS_TILE - 1)) / (float)GS_TILE);
+    r.maxy = (int)((pix_y + radius + (float)(GS_TILE - 1)) / (float)GS_TILE);
+    r.minx = min(gx, max(0, r.minx)); r.miny = min(gy, max(0, r.miny));
+    r.maxx = min(gx, max(0, r.maxx)); r.maxy = min(gy, max(0, r.maxy));
+    return r;
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const GsParams p, int32_t* __restrict__ radii)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)p.V * p.N) return;
+    const int v = (int)(gid / p.N), i = (int)(gid % p.N);
+    const float* __restrict__ cam = p.cams + (size_t)v * GS_CAM_FLOATS;
+    const float* V = cam + GS_CAM_VIEW;
+    const float* P = cam + GS_CAM_PROJ;
+    radii[gid] = 0;
+
+    const float px = p.means3D[3 * i], py = p.means3D[3 * i + 1], pz = p.means3D[3 * i + 2];
+    const float tx = V[0] * px + V[4] * py + V[8] * pz + V[12];
+    const float ty = V[1] * px + V[5] * py + V[9] * pz + V[13];
+    const float tz = V[2] * px + V[6] * py + V[10] * pz + V[14];
+    if (!(tz > GS_NEAR_CULL)) return;
+
+    const float hx = P[0] * px + P[4] * py + P[8] * pz + P[12];
+    const float hy = P[1] * px + P[5] * py + P[9] * pz + P[13];
+    const float hw = P[3] * px + P[7] * py + P[11] * pz + P[15];
+    const float pw = 1.0f / (hw + 0.0000001f);
+    const float ppx = hx * pw, ppy = hy * pw;
+
+    float c3[6];
+    if (p.cov3D) {
+        #pragma unroll
+        for (int k = 0; k < 6; k++) c3[k] = p.cov3D[6 * (size_t)i + k];
+    } else {
+        const float sx = p.mod * p.scales[3 * i], sy = p.mod * p.scales[3 * i + 1], sz = p.mod * p.scales[3 * i + 2];
+        const float4 q = reinterpret_cast<const float4*>(p.rots)[i];
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - r * z), R02 = 2.f * (x * z + r * y);
+        const float R10 = 2.f * (x * y + r * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - r * x);
+        const float R20 = 2.f * (x * z - r * y), R21 = 2.f * (y * z + r * x), R22 = 1.f - 2.f * (x * x + y * y);
+        const float A00 = R00 * sx, A01 = R01 * sy, A02 = R02 * sz;
+        const float A10 = R10 * sx, A11 = R11 * sy, A12 = R12 * sz;
+        const float A20 = R20 * sx, A21 = R21 * sy, A22 = R22 * sz;
+        c3[0] = A00 * A00 + A01 * A01 + A02 * A02;
+        c3[1] = A00 * A10 + A01 * A11 + A02 * A12;
+        c3[2] = A00 * A20 + A01 * A21 + A02 * A22;
+        c3[3] = A10 * A10 + A11 * A11 + A12 * A12;
+        c3[4] = A10 * A20 + A11 * A21 + A12 * A22;
+        c3[5] = A20 * A20 + A21 * A21 + A22 * A22;
+    }
+
+    const float tanx = cam[GS_CAM_TANFOVX], tany = cam[GS_CAM_TANFOVY];
+    const float fx = (float)p.W / (2.0f * tanx), fy = (float)p.H / (2.0f * tany);
+    const float limx = 1.3f * tanx, limy = 1.3f * tany;
+    const float txtz = tx / tz, tytz = ty / tz;
+    const float cx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+    const float cy = fminf(limy, fmaxf(-limy, tytz)) * tz;
+    const float J00 = fx / tz, J02 = -(fx * cx) / (tz * tz);
+    const float J11 = fy / tz, J12 = -(fy * cy) / (tz * tz);
+    float T0[3], T1[3];
+    #pragma unroll
+    for (int j = 0; j < 3; j++) {
+        T0[j] = J00 * V[4 * j + 0] + J02 * V[4 * j + 2];
+        T1[j] = J11 * V[4 * j + 1] + J12 * V[4 * j + 2];
+    }
+    const float S[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+    float X0[3], X1[3];
+    #pragma unroll
+    for (int j = 0; j < 3; j++) {
+        X0[j] = T0[0] * S[0][j] + T0[1] * S[1][j] + T0[2] * S[2][j];
+        X1[j] = T1[0] * S[0][j] + T1[1] * S[1][j] + T1[2] * S[2][j];
+    }
+    const float a = (X0[0] * T0[0] + X0[1] * T0[1] + X0[2] * T0[2]) + GS_LOWPASS;
+    const float b = X0[0] * T1[0] + X0[1] * T1[1] + X0[2] * T1[2];
+    const float c = (X1[0] * T1[0] + X1[1] * T1[1] + X1[2] * T1[2]) + GS_LOWPASS;
+
+    const float det = a * c - b * b;
+    if (!(det != 0.0f)) return;
+    const float det_inv = 1.0f / det;
+    const float cA = c * det_inv, cB = -b * det_inv, cC = a * det_inv;
+    const float mid = 0.5f * (a + c);
+    const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+    const float l1 = mid + sq, l2 = mid - sq;
+    const float radius = ceilf(3.0f * sqrtf(fmaxf(l1, l2)));
+    if (!(radius < 1.0e9f)) return;
+    const float pix_x = ((ppx + 1.0f) * (float)p.W - 1.0f) * 0.5f;
+    const float pix_y = ((ppy + 1.0f) * (float)p.H - 1.0f) * 0.5f;
+    if (!(fabsf(pix_x) < 1.0e9f) || !(fabsf(pix_y) < 1.0e9f)) return;
+
+    const Rect rc = tile_rect(pix_x, pix_y, radius, p.tiles_x, p.tiles_y);
+    if ((rc.maxx - rc.minx) * (rc.maxy - rc.miny) == 0) return;
+
+    float rgb[3];
+    unsigned clampbits = 0;
+    if (p.shs) {
+        const float* __restrict__ sh = p.shs + (size_t)i * p.M * 3;
+        const float dx = px - cam[GS_CAM_CAMPOS], dy = py - cam[GS_CAM_CAMPOS + 1], dz = pz - cam[GS_CAM_CAMPOS + 2];
+        const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float x = dx / len, y = dy / len, z = dz / len;
+        #pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            float res = kC0 * sh[0 * 3 + ch];
+            if (p.deg > 0) {
+                res = res - kC1 * y * sh[1 * 3 + ch] + kC1 * z * sh[2 * 3 + ch] - kC1 * x * sh[3 * 3 + ch];
+                if (p.deg > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    res = res + kC2[0] * xy * sh[4 * 3 + ch] + kC2[1] * yz * sh[5 * 3 + ch]
+                              + kC2[2] * (2.0f * zz - xx - yy) * sh[6 * 3 + ch]
+                              + kC2[3] * xz * sh[7 * 3 + ch] + kC2[4] * (xx - yy) * sh[8 * 3 + ch];
+                    if (p.deg > 2) {
+                        res = res + kC3[0] * y * (3.0f * xx - yy) * sh[9 * 3 + ch]
+                                  + kC3[1] * xy * z * sh[10 * 3 + ch]
+                                  + kC3[2] * y * (4.0f * zz - xx - yy) * sh[11 * 3 + ch]
+                                  + kC3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12 * 3 + ch]
+                                  + kC3[4] * x * (4.0f * zz - xx - yy) * sh[13 * 3 + ch]
+                                  + kC3[5] * z * (xx - yy) * sh[14 * 3 + ch]
+                                  + kC3[6] * x * (xx - 3.0f * yy) * sh[15 * 3 + ch];
+                    }
+                }
+            }
+            res += 0.5f;
+            if (res < 0.0f) { clampbits |= 1u << ch; res = 0.0f; }
+            rgb[ch] = res;
+        }
+    } else {
+        rgb[0] = p.colors[3 * i]; rgb[1] = p.colors[3 * i + 1]; rgb[2] = p.colors[3 * i + 2];
+    }
+
+    radii[gid] = (int)radius;
+    p.clamped[gid] = (uint8_t)clampbits;
+    float4* g = p.geom + gid * 3;
+    g[0] = make_float4(pix_x, pix_y, cA, cB);
+    g[1] = make_float4(cC, p.opac[i], tz, __int_as_float(i));
+    g[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+
+    // count this splat in every tile of its rectangle
+    uint32_t* cnt = p.tile_count + (size_t)v * p.tiles;
+    for (int y = rc.miny; y < rc.maxy; y++)
+        for (int x = rc.minx; x < rc.maxx; x++) atomicAdd(cnt + y * p.tiles_x + x, 1u);
+}
+
+// K3: write (depth_bits<<32 | id) into the tile's segment.  Slot order inside a tile is arbitrary
+// (atomic cursor); the per-tile sort restores (depth, id) order, a total order on distinct keys.
+__global__ void __launch_bounds__(256) scatter_kernel(const GsParams p, const int32_t* __restrict__ radii)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)p.V * p.N) return;
+    const int rad = radii[gid];
+    if (rad <= 0) return;
+    const int v = (int)(gid / p.N), i = (int)(gid % p.N);
+    const float4 g0 = p.geom[gid * 3], g1 = p.geom[gid * 3 + 1];
+    const Rect rc = tile_rect(g0.x, g0.y, (float)rad, p.tiles_x, p.tiles_y);
+    const unsigned long long pair = ((unsigned long long)__float_as_uint(g1.z) << 32) | (unsigned)i;
+    const size_t tbase = (size_t)v * p.tiles;
+    for (int y = rc.miny; y < rc.maxy; y++)
+        for (int x = rc.minx; x < rc.maxx; x++) {
+            const size_t t = tbase + y * p.tiles_x + x;
+            const unsigned long long pos = (unsigned long long)p.tile_start[t] + atomicAdd(p.tile_fill + t, 1u);
+            if (pos < (unsigned long long)p.cap) p.pairs[pos] = pair;
+        }
+}
+
+__global__ void mark_visible_kernel(int N, const float* __restrict__ means3D, const float* __restrict__ cam,
+                                    uint8_t* __restrict__ visible)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float* V = cam + GS_CAM_VIEW;
+    const float tz = V[2] * means3D[3 * i] + V[6] * means3D[3 * i + 1] + V[10] * means3D[3 * i + 2] + V[14];
+    visible[i] = tz > GS_NEAR_CULL;
+}
+
+}  // namespace
+
+void gs_launch_preprocess(const GsParams& p, int32_t* radii, cudaStream_t s)
+{
+    const long long n = (long long)p.V * p.N;
+    if (n == 0) return;
+    preprocess_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, radii);
+}
+
+void gs_launch_scatter(const GsParams& p, const int32_t* radii, cudaStream_t s)
+{
+    const long long n = (long long)p.V * p.N;
+    if (n == 0) return;
+    scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, radii);
+}
+
+void gs_launch_mark_visible(int N, const float* means3D, const float* cam, uint8_t* visible, cudaStream_t s)
+{
+    if (N == 0) return;
+    mark_visible_kernel<<<(N + 255) / 256, 256, 0, s>>>(N, means3D, cam, visible);
+}

@@ -1,0 +1,249 @@
+"""Functional host layer over the C ABI: tensors in, tensors out, no autograd.
+
+PyTorch is plumbing here (device memory, streams); every kernel on this path lives in
+libtopo4d_b200.so.  One call renders V camera views of the same Gaussians (the reference renders
+one view per call -- train.py:307 -- which is V = 1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GS_CAM_FLOATS, GsBackwardIO, GsForwardOut, GsProblem, GsStatus, GsWorkspaceView
+
+# remembered instance capacity per problem shape (grown on overflow)
+_CAP_MEMO: dict[tuple, int] = {}
+
+
+def _ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor | None, dev) -> torch.Tensor | None:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or t.device != dev:
+        t = t.to(device=dev, dtype=torch.float32)
+    return t.contiguous()
+
+
+def pack_cameras_numpy(cams, bg=(0.0, 0.0, 0.0)) -> np.ndarray:
+    """List of synth.Camera-like objects (viewmatrix, projmatrix, campos, tanfovx, tanfovy) -> [V,48] float32."""
+    out = np.zeros((len(cams), GS_CAM_FLOATS), np.float32)
+    for i, c in enumerate(cams):
+        out[i, 0:16] = np.asarray(c.viewmatrix, np.float32).reshape(16)
+        out[i, 16:32] = np.asarray(c.projmatrix, np.float32).reshape(16)
+        out[i, 32:35] = np.asarray(c.campos, np.float32).reshape(3)
+        out[i, 35:38] = np.asarray(bg, np.float32).reshape(3)
+        out[i, 38] = c.tanfovx
+        out[i, 39] = c.tanfovy
+    return out
+
+
+@dataclass
+class RasterState:
+    """Everything backward needs; owns the workspace so concurrent forwards never alias."""
+    problem: GsProblem
+    workspace: torch.Tensor
+    keep: tuple                      # input tensors kept alive (their pointers sit in `problem`)
+    radii: torch.Tensor
+    N: int
+    V: int
+    H: int
+    W: int
+    M: int
+    use_sh: bool
+    use_cov: bool
+    device: torch.device
+    _status: GsStatus | None = field(default=None, repr=False)
+
+    def status(self) -> GsStatus:
+        """Synchronising read of the device status block (num_rendered, overflow, longest tile list)."""
+        if self._status is None:
+            st = GsStatus()
+            with torch.cuda.device(self.device):
+                code = _lib.lib().gs_read_status(C.byref(self.problem), C.byref(st),
+                                                 C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            if code not in (_lib.GS_OK, _lib.GS_E_OVERFLOW):
+                _lib.check(code, "gs_read_status")
+            self._status = st
+        return self._status
+
+    def view(self) -> dict:
+        """Index structures / per-pixel state as tensors (clones), for the bit-exact parity tests."""
+        wv = GsWorkspaceView()
+        _lib.check(_lib.lib().gs_workspace_view(C.byref(self.problem), C.byref(wv)), "gs_workspace_view")
+        base = self.workspace.data_ptr()
+        T = wv.tiles_x * wv.tiles_y * self.V
+        I = min(int(self.status().num_instances), int(self.problem.cap_instances))
+
+        def sl(ptr, nbytes, dtype):
+            off = ptr - base
+            return self.workspace[off:off + nbytes].view(dtype).clone()
+        VN = self.V * max(self.N, 1)
+        return dict(
+            tile_start=sl(wv.tile_start, 4 * (T + 1), torch.int32),
+            sorted_ids=sl(wv.sorted_ids, 4 * I, torch.int32),
+            sorted_records=sl(wv.sorted_records, 48 * I, torch.float32).view(-1, 12),
+            geom_records=sl(wv.geom_records, 48 * VN, torch.float32).view(self.V, -1, 12),
+            final_T=sl(wv.final_T, 4 * self.V * self.H * self.W, torch.float32).view(self.V, self.H, self.W),
+            n_contrib=sl(wv.n_contrib, 4 * self.V * self.H * self.W, torch.int32).view(self.V, self.H, self.W),
+            grad2d=sl(wv.grad2d, 48 * VN, torch.float32).view(self.V, -1, 12),
+            tiles_x=wv.tiles_x, tiles_y=wv.tiles_y, num_instances=int(self.status().num_instances))
+
+
+def _check_pairs(shs, colors_precomp, scales, rotations, cov3D_precomp):
+    # same messages (typo included) as the upstream Python wrapper the reference imports (train.py:19)
+    if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+        raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+    if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+            ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+        raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+
+def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None, colors_precomp=None,
+            scales=None, rotations=None, cov3D_precomp=None, sh_degree=0, scale_modifier=1.0, debug=False,
+            check="sync", cap_instances=None):
+    """Render V views.  `cameras`: [V,48] float32 CUDA tensor (see include/topo4d_b200.h GS_CAM_*).
+
+    check: "sync"  -> read the status block after the launch (one small D2H, like upstream's
+                      num_rendered read) and transparently re-run with a larger capacity on overflow;
+           "none"  -> fully asynchronous; call ``state.status()`` later to validate.
+    Returns (color[V,3,H,W], radii[V,N] i32, depth[V,1,H,W], alpha[V,1,H,W], RasterState)."""
+    _check_pairs(shs, colors_precomp, scales, rotations, cov3D_precomp)
+    if not means3D.is_cuda:
+        raise RuntimeError("topo4d_b200: the rasterizer is CUDA-only (means3D is on %s); there is no CPU path" % means3D.device)
+    L = _lib.lib()
+    dev = means3D.device
+    H, W = int(image_height), int(image_width)
+    means3D = _f32c(means3D, dev)
+    N = int(means3D.shape[0])
+    opacities = _f32c(opacities, dev)
+    shs = _f32c(shs, dev)
+    colors_precomp = _f32c(colors_precomp, dev)
+    scales, rotations, cov3D_precomp = _f32c(scales, dev), _f32c(rotations, dev), _f32c(cov3D_precomp, dev)
+    cameras = _f32c(cameras, dev).reshape(-1, GS_CAM_FLOATS)
+    V = int(cameras.shape[0])
+    M = 0 if shs is None else int(shs.reshape(N, -1, 3).shape[1]) if N > 0 else int(shs.shape[1])
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    color = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev)
+    depth = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
+    alpha = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
+    radii = torch.empty((V, max(N, 1)), dtype=torch.int32, device=dev)
+    out = GsForwardOut(_ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii))
+
+    key = (N, V, H, W, dev.index)
+    cap = int(cap_instances) if cap_instances is not None else _CAP_MEMO.get(key)
+
+    def make_problem(cap_):
+        nbytes = L.gs_workspace_bytes(N, V, H, W, cap_)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        pr = GsProblem(N, V, H, W, int(sh_degree), M, float(scale_modifier), int(bool(debug)), cap_,
+                       _ptr(means3D), _ptr(shs), _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
+                       _ptr(cov3D_precomp), _ptr(cameras), _ptr(ws), nbytes)
+        return pr, ws
+
+    with torch.cuda.device(dev):
+        if cap is None:
+            # first call for this shape: exact count from a preprocess-only pass
+            pr, ws = make_problem(0)
+            n = C.c_int64(0)
+            _lib.check(L.gs_count_instances(C.byref(pr), C.byref(n), stream), "gs_count_instances")
+            cap = int(n.value * 1.25) + 4096
+        while True:
+            pr, ws = make_problem(cap)
+            _lib.check(L.gs_forward(C.byref(pr), C.byref(out), stream), "gs_forward")
+            state = RasterState(pr, ws, (means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, cameras),
+                                radii, N, V, H, W, M, shs is not None, cov3D_precomp is not None, dev)
+            if check != "sync":
+                break
+            st = state.status()
+            if not st.overflow:
+                break
+            cap = int(st.num_instances * 1.25) + 4096
+    if cap_instances is None:
+        _CAP_MEMO[key] = max(cap, _CAP_MEMO.get(key, 0))
+    return color, radii[:, :N], depth, alpha, state
+
+
+@dataclass
+class GradBundle:
+    """Gradients of one backward: `flat` is ONE contiguous fp32 buffer (all-reduce-ready), the named
+    tensors are views into it."""
+    flat: torch.Tensor
+    means3D: torch.Tensor
+    means2D: torch.Tensor
+    opacities: torch.Tensor
+    shs: torch.Tensor | None = None
+    colors_precomp: torch.Tensor | None = None
+    scales: torch.Tensor | None = None
+    rotations: torch.Tensor | None = None
+    cov3D_precomp: torch.Tensor | None = None
+
+
+def _al4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None, flat: torch.Tensor | None = None) -> GradBundle:
+    """Gradients summed over the V views of `state`.  dL_dcolor [V,3,H,W] (or [3,H,W] when V == 1)."""
+    L = _lib.lib()
+    dev, N, V, H, W, M = state.device, state.N, state.V, state.H, state.W, state.M
+    dL_dcolor = _f32c(dL_dcolor, dev)
+    dL_ddepth = _f32c(dL_ddepth, dev)
+    dL_dalpha = _f32c(dL_dalpha, dev)
+    assert dL_dcolor.numel() == V * 3 * H * W, "dL_dcolor must be [V,3,H,W]"
+    ncol = N * M * 3 if state.use_sh else N * 3
+    sizes = [("means3D", N * 3), ("means2D", N * 3), ("color", ncol), ("opacities", N),
+             ("a", N * 6 if state.use_cov else N * 3), ("b", 0 if state.use_cov else N * 4)]
+    offs, o = {}, 0
+    for name, n in sizes:
+        offs[name] = (o, n)
+        o += _al4(n)
+    total = max(o, 4)
+    if flat is None:
+        flat = torch.zeros(total, dtype=torch.float32, device=dev) if N == 0 else \
+            torch.empty(total, dtype=torch.float32, device=dev)
+    else:
+        assert flat.numel() >= total and flat.is_contiguous() and flat.device == dev
+    seg = {k: flat[s:s + n] for k, (s, n) in offs.items()}
+    io = GsBackwardIO(_ptr(dL_dcolor), _ptr(dL_ddepth), _ptr(dL_dalpha), _ptr(state.radii),
+                      _ptr(seg["means3D"]), _ptr(seg["means2D"]),
+                      _ptr(seg["color"]) if state.use_sh else None, None if state.use_sh else _ptr(seg["color"]),
+                      _ptr(seg["opacities"]),
+                      None if state.use_cov else _ptr(seg["a"]), None if state.use_cov else _ptr(seg["b"]),
+                      _ptr(seg["a"]) if state.use_cov else None)
+    if N > 0:
+        with torch.cuda.device(dev):
+            _lib.check(L.gs_backward(C.byref(state.problem), C.byref(io),
+                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "gs_backward")
+    g = GradBundle(flat=flat, means3D=seg["means3D"].view(N, 3), means2D=seg["means2D"].view(N, 3),
+                   opacities=seg["opacities"].view(N, 1))
+    if state.use_sh:
+        g.shs = seg["color"].view(N, M, 3)
+    else:
+        g.colors_precomp = seg["color"].view(N, 3)
+    if state.use_cov:
+        g.cov3D_precomp = seg["a"].view(N, 6)
+    else:
+        g.scales = seg["a"].view(N, 3)
+        g.rotations = seg["b"].view(N, 4)
+    return g
+
+
+def mark_visible(positions: torch.Tensor, camera: torch.Tensor) -> torch.Tensor:
+    dev = positions.device
+    if not positions.is_cuda:
+        raise RuntimeError("topo4d_b200: markVisible is CUDA-only")
+    pos = _f32c(positions, dev)
+    cam = _f32c(camera, dev).reshape(-1)[:GS_CAM_FLOATS]
+    vis = torch.empty(pos.shape[0], dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().gs_mark_visible(pos.shape[0], _ptr(pos), _ptr(cam), _ptr(vis),
+                                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "gs_mark_visible")
+    return vis.bool()

@@ -1,0 +1,125 @@
+"""Drop-in operator surface: ``GaussianRasterizationSettings`` / ``GaussianRasterizer``.
+
+Mirrors the interface of the `diff_gaussian_rasterization` package the reference imports
+(train.py:19, helpers.py:18-19): settings built at helpers.py:73-86, call at train.py:307
+``Renderer(raster_settings=cam)(**rendervar)`` with the kwargs of helpers.py:91-112, returning
+``(color[3,H,W], radii[N] int32, depth[1,H,W], alpha[1,H,W])``; backward fills gradients for
+(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3D_precomp), with
+``means2D.grad`` the NDC-scaled screen-space gradient the reference retains (train.py:304).
+Adds ``render_views`` -- the same op over V cameras in one launch sequence (view-parallel path).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import engine
+from ._lib import GS_CAM_FLOATS
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+_CAM_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CAM_CACHE_MAX = 256
+
+
+def pack_settings(rs: GaussianRasterizationSettings) -> torch.Tensor:
+    """Settings -> one [48] float32 device block (cached: the reference builds 24 settings per
+    frame and reuses each for thousands of iterations, train.py:98,661)."""
+    tens = (rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg)
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride())) for t in tens) + \
+        (float(rs.tanfovx), float(rs.tanfovy))
+    hit = _CAM_CACHE.get(key)
+    if hit is not None:
+        _CAM_CACHE.move_to_end(key)
+        return hit[0]
+    dev = rs.viewmatrix.device
+    f = lambda t, n: t.to(device=dev, dtype=torch.float32).reshape(-1)[:n]
+    tail = torch.zeros(GS_CAM_FLOATS - 38, dtype=torch.float32)
+    tail[0], tail[1] = float(rs.tanfovx), float(rs.tanfovy)
+    packed = torch.cat([f(rs.viewmatrix.contiguous(), 16), f(rs.projmatrix.contiguous(), 16), f(rs.campos, 3), f(rs.bg, 3),
+                        tail.to(dev)]).contiguous()
+    _CAM_CACHE[key] = (packed, tens)         # keep the source tensors alive so data_ptr keys stay unique
+    if len(_CAM_CACHE) > _CAM_CACHE_MAX:
+        _CAM_CACHE.popitem(last=False)
+    return packed
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """V-view op.  Outputs carry the leading V dimension; the single-view wrapper strips it."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                cameras, image_height, image_width, sh_degree, scale_modifier, debug):
+        color, radii, depth, alpha, state = engine.forward(
+            means3D, opacities, cameras, image_height, image_width, shs=sh, colors_precomp=colors_precomp,
+            scales=scales, rotations=rotations, cov3D_precomp=cov3Ds_precomp, sh_degree=sh_degree,
+            scale_modifier=scale_modifier, debug=debug, check="sync")
+        ctx.state = state
+        ctx.shapes = tuple(None if t is None else t.shape for t in
+                           (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
+        state = ctx.state
+        g = engine.backward(state, grad_color, grad_depth, grad_alpha)
+        s = ctx.shapes
+        rs = lambda t, shp: None if (t is None or shp is None) else t.reshape(shp)
+        return (rs(g.means3D, s[0]), rs(g.means2D, s[1]), rs(g.shs, s[2]), rs(g.colors_precomp, s[3]),
+                rs(g.opacities, s[4]), rs(g.scales, s[5]), rs(g.rotations, s[6]), rs(g.cov3D_precomp, s[7]),
+                None, None, None, None, None, None)
+
+
+def _none_if_empty(t):
+    return None if (t is None or (torch.is_tensor(t) and t.numel() == 0 and t.dim() <= 1)) else t
+
+
+def render_views(cameras: torch.Tensor, image_height: int, image_width: int, means3D, means2D, opacities, *,
+                 shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, sh_degree=0,
+                 scale_modifier=1.0, debug=False):
+    """All V views of `cameras` [V,48] in one pass; returns (color[V,3,H,W], radii[V,N], depth[V,1,H,W],
+    alpha[V,1,H,W]); gradients are summed over the views."""
+    if means2D is None:
+        means2D = torch.zeros_like(means3D)
+    return _RasterizeGaussians.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                     cov3D_precomp, cameras, image_height, image_width, sh_degree, scale_modifier, debug)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            return engine.mark_visible(positions, pack_settings(self.raster_settings))
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        shs, colors_precomp = _none_if_empty(shs), _none_if_empty(colors_precomp)
+        scales, rotations, cov3D_precomp = _none_if_empty(scales), _none_if_empty(rotations), _none_if_empty(cov3D_precomp)
+        engine._check_pairs(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        cam = pack_settings(rs).reshape(1, GS_CAM_FLOATS)
+        color, radii, depth, alpha = _RasterizeGaussians.apply(
+            means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cam,
+            int(rs.image_height), int(rs.image_width), int(rs.sh_degree), float(rs.scale_modifier), bool(rs.debug))
+        return color[0], radii[0], depth[0], alpha[0]
