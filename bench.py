@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd Mpixels/s of the Gaussian rasterizer on BASELINE.json config 2
+(24 views 1920x1080, ~60k mesh-bound Gaussians, SH degree 3, depth+alpha consumed).
+
+  python bench.py --gpus 1 --steps K --warmup W            # our sm_100a path
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # view-parallel, strong scaling
+  python bench.py --impl reference ...                     # the CPU oracle port on the host cores
+
+A "step" = one pass of the hot path over all 24 camera views: forward (preprocess -> tile-bin -> blend)
+and backward (blend-bwd -> preprocess-bwd) for every view, gradients summed over views; with N > 1 GPUs
+rank r owns views {r, r+N, ...} and the step ends with ONE NCCL all-reduce of the flat gradient buffer.
+Prints one JSON line on rank 0 (contract in the task statement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fwd+bwd Mpixels/s @24x1080p/60k Gaussians"
+UNIT = "Mpixels/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--views", type=int, default=24)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--gaussians", type=int, default=60000)
+    ap.add_argument("--sh-degree", type=int, default=3)
+    ap.add_argument("--opacity", default="topo4d", choices=["topo4d", "generic"])
+    ap.add_argument("--views-per-launch", type=int, default=0, help="0 = all local views in one launch sequence")
+    ap.add_argument("--cpu-sample-views", type=int, default=24, help="views in the cpu_baseline sample (ours arm)")
+    ap.add_argument("--ref-views-per-step", type=int, default=4, help="views per step of the --impl reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(a):
+    from topo4d_b200 import synth
+    scene = synth.head_scene(a.gaussians, seed=0, sh_degree=a.sh_degree, opacity=a.opacity)
+    cams = synth.ring_cameras(a.views, w=a.width, h=a.height)
+    return scene, cams
+
+
+def config_dict(a, extra=None):
+    d = {"workload": f"BASELINE config 2: {a.views} views {a.width}x{a.height}, {a.gaussians} mesh-bound Gaussians "
+                     f"(head ellipsoid), SH degree {a.sh_degree}, opacity regime '{a.opacity}', depth+alpha consumed",
+         "views": a.views, "width": a.width, "height": a.height, "gaussians": a.gaussians, "sh_degree": a.sh_degree,
+         "l2": "per-step pixel streams (~2.8 GB over 24 views) exceed the 126 MB L2; no explicit flush"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference rasterizer is CUDA-only and un-vendored: no reference CPU path)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(scene, cams, a, n_views, rng):
+    """fwd+bwd of `n_views` views on the host cores through oracle/gs_oracle.c; returns seconds."""
+    from oracle import gs_oracle
+    H, W = a.height, a.width
+    gC = rng.normal(size=(3, H, W)).astype(np.float32) / (3 * H * W)
+    gD = np.full((H, W), 0.1 / (H * W), np.float32)
+    gA = np.full((H, W), 0.1 / (H * W), np.float32)
+    t0 = time.perf_counter()
+    for cam in cams[:n_views]:
+        _, _, _, _, st = gs_oracle.forward(scene["means3D"], scene["opacities"], shs=scene.get("shs"),
+                                           colors_precomp=scene.get("colors_precomp"), scales=scene["scales"],
+                                           rotations=scene["rotations"], image_height=H, image_width=W,
+                                           tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=np.zeros(3, np.float32),
+                                           viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, campos=cam.campos,
+                                           sh_degree=a.sh_degree if "shs" in scene else 0)
+        st.backward(gC, gD, gA)
+    return time.perf_counter() - t0
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import gs_oracle
+    scene, cams = workload(a)
+    rng = np.random.default_rng(0)
+    nv = max(1, min(a.ref_views_per_step, a.views))
+    for _ in range(min(a.warmup, 1)):
+        cpu_sample(scene, cams, a, 1, rng)
+    total = 0.0
+    for _ in range(a.steps):
+        total += cpu_sample(scene, cams, a, nv, rng)
+    mpix = a.steps * nv * a.width * a.height / 1e6 / total
+    cores = gs_oracle.num_threads()
+    sample = f"{nv} of the {a.views} views per step (fwd+bwd, 1080p, all Gaussians), {a.steps} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(a, {"note": "reference rasterizer is CUDA-only and not vendored; this arm is the CPU "
+                                              "oracle port (oracle/gs_oracle.c, OpenMP over tiles)"}),
+            "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.time(), ln.strip()))
+
+    def mark(self, which):
+        setattr(self, which, time.time())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e18)] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from topo4d_b200 import engine, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    scene, cams = workload(a)
+    my_views = parallel.shard_views(a.views, rank, world)
+    H, W = a.height, a.width
+    vpl = a.views_per_launch if a.views_per_launch > 0 else len(my_views)
+    groups = [my_views[i:i + vpl] for i in range(0, len(my_views), vpl)]
+
+    # pinned host copies of the per-step inputs (the Gaussian parameters) for the e2e leg
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in scene.items()}
+    t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    cam_all = torch.tensor(engine.pack_cameras_numpy(cams, (0.0, 0.0, 0.0)), device=dev)
+    cam_groups = [cam_all[g].contiguous() for g in groups]
+    use_sh = "shs" in t
+
+    def fwd(g, params, ev=None):
+        return engine.forward(params["means3D"], params["opacities"], cam_groups[g], H, W, shs=params.get("shs"),
+                              colors_precomp=params.get("colors_precomp"), scales=params["scales"],
+                              rotations=params["rotations"], sh_degree=a.sh_degree if use_sh else 0, check="none",
+                              cap_instances=caps[g], stage_events=ev)
+
+    # size capacities once (synchronising) and build the fixed dL/dpixel images of
+    # L = L1(color, target) + 0.1 mean(depth) + 0.1 mean(alpha)  (SSIM excluded)
+    caps, gimgs, stats = [None] * len(groups), [], {"num_rendered": 0, "max_tile": 0}
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    for g in range(len(groups)):
+        color, radii, depth, alpha, st = engine.forward(t["means3D"], t["opacities"], cam_groups[g], H, W, shs=t.get("shs"),
+                                                        colors_precomp=t.get("colors_precomp"), scales=t["scales"],
+                                                        rotations=t["rotations"], sh_degree=a.sh_degree if use_sh else 0)
+        s = st.status()
+        caps[g] = int(s.num_instances * 1.1) + 4096
+        stats["num_rendered"] += int(s.num_instances)
+        stats["max_tile"] = max(stats["max_tile"], int(s.max_tile_instances))
+        target = torch.rand(color.shape, device=dev, generator=gen)
+        nv = len(groups[g])
+        gimgs.append((torch.sign(color - target) / (3 * H * W), torch.full_like(depth, 0.1 / (H * W)),
+                      torch.full_like(alpha, 0.1 / (H * W))))
+        del color, depth, alpha, st, target
+    flat = None
+
+    def step(params, ev=None):
+        nonlocal flat
+        total = None
+        for g in range(len(groups)):
+            *_, st = fwd(g, params, ev)
+            gb = engine.backward(st, *gimgs[g], stage_events=ev)
+            total = gb.flat if total is None else total.add_(gb.flat)
+        flat = total
+        if world > 1:
+            parallel.allreduce_flat_(flat)
+        return flat
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(a.warmup, 3)):
+        step(t)
+    barrier()
+    # ---- timed region: K steps, device-timed, per-stage events on the launching stream ----
+    ev = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.mark("t0")
+    e0.record()
+    for _ in range(a.steps):
+        step(t, ev)
+    e1.record()
+    barrier()
+    if sampler:
+        sampler.mark("t1")
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    stage_ms = {k: float(np.mean([x.elapsed_time(y) for x, y in v])) for k, v in ev.items()}      # per launch
+    stage_share = {k: float(np.sum([x.elapsed_time(y) for x, y in v])) / e0.elapsed_time(e1) for k, v in ev.items()}
+
+    # ---- e2e: same step through the public API with HOST buffers: H2D of the parameters, D2H of the gradients ----
+    e2e = None
+    if not a.no_e2e:
+        grads_host = torch.empty(flat.numel(), dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * 4 for v in host.values())
+        d2h = grads_host.numel() * 4
+        for _ in range(2):
+            p = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            grads_host.copy_(step(p), non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(a.steps):
+            p = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            grads_host.copy_(step(p), non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the caller needs the gradients on the host every step
+        f1.record()
+        barrier()
+        ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e = {"value": a.steps * a.views * H * W / 1e6 / (float(ms2.item()) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    clocks = sampler.stop() if sampler else None
+
+    # overflow check after the timed region (capacity was fixed; the flag is sticky per workspace)
+    *_, st = fwd(0, t)
+    assert not st.status().overflow, "instance capacity overflow during the benchmark"
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
+        # algorithmic bytes of the dominant kernel per launch: blend fwd = I*44 + P*28
+        I_local = stats["num_rendered"] / max(len(groups), 1)
+        P_launch = vpl * H * W
+        bw = {}
+        alg = {"blend_fwd": I_local * 44 + P_launch * 28, "blend_bwd": I_local * 84 + P_launch * 28}
+        for k, b in alg.items():
+            if k in stage_ms and stage_ms[k] > 0:
+                bw[k] = b / (stage_ms[k] * 1e-3) / 1e9
+        dom = max(("blend_fwd", "blend_bwd"), key=lambda k: stage_ms.get(k, 0.0))
+        roof = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": bw.get(dom), "peak": peak, "unit": "GB/s",
+                "frac": (bw.get(dom) or 0.0) / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom], "launch_ms": stage_ms.get(dom),
+                "N": a.gaussians, "I_per_launch": I_local, "P_per_launch": P_launch,
+                "all_stage_ms_per_launch": stage_ms, "stage_share_of_step": stage_share,
+                "blend_fwd_gbs": bw.get("blend_fwd"), "blend_bwd_gbs": bw.get("blend_bwd")}
+        launches = a.steps * len(groups) * (engine.KERNELS_PER_FORWARD + engine.KERNELS_PER_BACKWARD)
+        value = a.steps * a.views * H * W / 1e6 / (ms_total / 1e3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": config_dict(a, {"views_per_rank": len(my_views), "views_per_launch": vpl,
+                                          "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of the flat fp32 gradient buffer per step",
+                                          "num_rendered_rank0": stats["num_rendered"], "max_tile_instances": stats["max_tile"]}),
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof}
+        if world == 1 and not a.no_cpu_baseline:
+            nv = max(1, min(a.cpu_sample_views, a.views))
+            from oracle import gs_oracle
+            sec = cpu_sample(scene, cams, a, nv, np.random.default_rng(0))
+            line["cpu_baseline"] = {"value": nv * H * W / 1e6 / sec, "unit": UNIT, "cores": gs_oracle.num_threads(),
+                                    "kind": "port", "sample": f"{nv} of the {a.views} views, fwd+bwd, {sec:.1f} s on the host cores "
+                                                              "(oracle/gs_oracle.c, OpenMP over tiles)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -117,6 +117,20 @@ int gs_forward(const GsProblem* p, const GsForwardOut* out, gs_stream_t stream);
 /* Backward for the same V views; needs the workspace exactly as forward left it. */
 int gs_backward(const GsProblem* p, const GsBackwardIO* io, gs_stream_t stream);
 
+/* The same pipelines one stage at a time (bit mask, stages run in pipeline order), so a caller can put
+ * CUDA events between kernels on its own stream (bench.py's per-kernel roofline timing does).
+ * gs_forward == gs_forward_stages(GS_FWD_ALL), gs_backward == gs_backward_stages(GS_BWD_ALL). */
+#define GS_FWD_PREPROCESS 1u        /* status/histogram reset + preprocess + tile scan */
+#define GS_FWD_SCATTER    2u        /* (depth,id) pairs into tile segments */
+#define GS_FWD_SORT       4u        /* per-tile sort + record gather */
+#define GS_FWD_BLEND      8u        /* front-to-back blend */
+#define GS_FWD_ALL       15u
+#define GS_BWD_BLEND      1u        /* grad2d reset + back-to-front blend backward */
+#define GS_BWD_PREPROCESS 2u        /* per-Gaussian chain rule, sums the V views */
+#define GS_BWD_ALL        3u
+int gs_forward_stages(const GsProblem* p, const GsForwardOut* out, uint32_t stages, gs_stream_t stream);
+int gs_backward_stages(const GsProblem* p, const GsBackwardIO* io, uint32_t stages, gs_stream_t stream);
+
 /* Copies the status block to the host (synchronises `stream`).  Returns GS_E_OVERFLOW if the
  * last forward needed more instances than the workspace holds (grow cap_instances, retry). */
 int gs_read_status(const GsProblem* p, GsStatus* status_host, gs_stream_t stream);

@@ -48,13 +48,14 @@ class GsOracleState:
 
     def __init__(self, handle, N, M, H, W, use_sh, use_cov):
         self._h = handle
+        self._free = _L().gso_free
         self.N, self.M, self.H, self.W = N, M, H, W
         self.use_sh, self.use_cov = use_sh, use_cov
         self.gx, self.gy = (W + 15) // 16, (H + 15) // 16
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            _L().gso_free(self._h)
+        if getattr(self, "_h", None) and getattr(self, "_free", None):
+            self._free(self._h)
             self._h = None
 
     @property

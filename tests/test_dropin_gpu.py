@@ -1,0 +1,82 @@
+"""GPU: the reference-facing Python surface (module name, kwargs, autograd contract)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity
+from topo4d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _settings(cam, bg, deg=0):
+    from diff_gaussian_rasterization import GaussianRasterizationSettings as Camera
+    dev = "cuda"
+    w2c = torch.tensor(cam.w2c, dtype=torch.float32, device=dev)
+    # exactly how the reference hands matrices over: non-contiguous transposed views (helpers.py:67-72)
+    view = w2c.unsqueeze(0).transpose(1, 2)
+    proj = torch.tensor(cam.projmatrix, device=dev).unsqueeze(0)
+    return Camera(image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                  bg=torch.tensor(bg, dtype=torch.float32, device=dev), scale_modifier=1.0, viewmatrix=view,
+                  projmatrix=proj, sh_degree=deg, campos=torch.tensor(cam.campos, device=dev), prefiltered=False, debug=False)
+
+
+def test_reference_call_pattern_train_py_307():
+    """im, radius, _, _ = Renderer(raster_settings=cam)(**rendervar); loss.backward(); means2D.grad retained."""
+    from diff_gaussian_rasterization import GaussianRasterizer as Renderer
+    sc = synth.random_scene(3000, seed=0)
+    cam = synth.front_camera(160, 120)
+    bg = (0.0, 0.0, 0.0)
+    params = {k: torch.tensor(v, device="cuda", requires_grad=True) for k, v in sc.items()}
+    rendervar = {
+        "means3D": params["means3D"], "colors_precomp": params["colors_precomp"],
+        "rotations": torch.nn.functional.normalize(params["rotations"]), "opacities": params["opacities"],
+        "scales": params["scales"],
+        "means2D": torch.zeros_like(params["means3D"], requires_grad=True, device="cuda") + 0,
+    }
+    rendervar["means2D"].retain_grad()
+    im, radius, depth, alpha = Renderer(raster_settings=_settings(cam, bg))(**rendervar)
+    assert im.shape == (3, 120, 160) and radius.shape == (3000,) and radius.dtype == torch.int32
+    assert depth.shape == (1, 120, 160) and alpha.shape == (1, 120, 160)
+    rng = np.random.default_rng(1)
+    gC = rng.normal(size=(1, 3, 120, 160)).astype(np.float32)
+    (im * torch.tensor(gC[0], device="cuda")).sum().backward()          # depth/alpha unused -> zero grads, like train.py
+    sc_o = dict(sc, rotations=rendervar["rotations"].detach().cpu().numpy())   # what the op actually received
+    ref, ref_g = parity.run_oracle(sc_o, [cam], 120, 160, 0, bg, gC, None, None)
+    assert np.abs(im.detach().cpu().numpy() - ref[0]["color"]).max() <= parity.ABS_TOL
+    assert (radius.cpu().numpy() == ref[0]["radii"]).all()
+    assert parity.grad_rel_err(rendervar["means2D"].grad.cpu().numpy(), ref_g["means2D"]) <= parity.REL_TOL
+    assert float(rendervar["means2D"].grad[:, 2].abs().max()) == 0.0
+    for k in ("means3D", "colors_precomp", "opacities", "scales"):
+        assert parity.grad_rel_err(params[k].grad.cpu().numpy().reshape(ref_g[k].shape), ref_g[k]) <= parity.REL_TOL, k
+    seen = radius > 0
+    assert bool(seen.any())
+
+
+def test_sh_path_markvisible_and_errors():
+    from diff_gaussian_rasterization import GaussianRasterizer as Renderer
+    sc = synth.random_scene(1000, seed=2, sh_degree=3)
+    cam = synth.make_camera(synth.look_at((2.0, 0.5, -3.0)), 96, 96, 100.0, 100.0)
+    t = {k: torch.tensor(v, device="cuda") for k, v in sc.items()}
+    r = Renderer(raster_settings=_settings(cam, (0.1, 0.2, 0.3), deg=3))
+    im, radius, _, _ = r(means3D=t["means3D"], means2D=torch.zeros_like(t["means3D"]), opacities=t["opacities"],
+                         shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+    ref, _ = parity.run_oracle(sc, [cam], 96, 96, 3, (0.1, 0.2, 0.3))
+    assert np.abs(im.cpu().numpy() - ref[0]["color"]).max() <= parity.ABS_TOL
+    from oracle import gs_oracle
+    vis = r.markVisible(t["means3D"])
+    assert vis.dtype == torch.bool and (vis.cpu().numpy() == gs_oracle.mark_visible(sc["means3D"], cam.viewmatrix)).all()
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(means3D=t["means3D"], means2D=None, opacities=t["opacities"], scales=t["scales"], rotations=t["rotations"])
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=t["means3D"], means2D=None, opacities=t["opacities"], shs=t["shs"], scales=t["scales"])
+
+
+def test_cpu_tensors_fail_loudly():
+    from diff_gaussian_rasterization import GaussianRasterizer as Renderer
+    sc = synth.random_scene(10, seed=0)
+    t = {k: torch.tensor(v) for k, v in sc.items()}
+    cam = synth.front_camera(32, 32)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        Renderer(raster_settings=_settings(cam, (0, 0, 0)))(means3D=t["means3D"], means2D=None, opacities=t["opacities"],
+                                                            colors_precomp=t["colors_precomp"], scales=t["scales"], rotations=t["rotations"])

@@ -11,6 +11,8 @@ import os
 from . import build as _build
 
 GS_CAM_FLOATS = 48
+GS_FWD_PREPROCESS, GS_FWD_SCATTER, GS_FWD_SORT, GS_FWD_BLEND, GS_FWD_ALL = 1, 2, 4, 8, 15
+GS_BWD_BLEND, GS_BWD_PREPROCESS, GS_BWD_ALL = 1, 2, 3
 GS_OK, GS_E_BAD_ARGS, GS_E_WORKSPACE_SMALL, GS_E_CUDA, GS_E_OVERFLOW, GS_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 _vp = C.c_void_p
@@ -50,6 +52,8 @@ SYMBOLS = {
     "gs_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
     "gs_forward": (C.c_int, [C.POINTER(GsProblem), C.POINTER(GsForwardOut), _vp]),
     "gs_backward": (C.c_int, [C.POINTER(GsProblem), C.POINTER(GsBackwardIO), _vp]),
+    "gs_forward_stages": (C.c_int, [C.POINTER(GsProblem), C.POINTER(GsForwardOut), C.c_uint32, _vp]),
+    "gs_backward_stages": (C.c_int, [C.POINTER(GsProblem), C.POINTER(GsBackwardIO), C.c_uint32, _vp]),
     "gs_read_status": (C.c_int, [C.POINTER(GsProblem), C.POINTER(GsStatus), _vp]),
     "gs_count_instances": (C.c_int, [C.POINTER(GsProblem), C.POINTER(C.c_int64), _vp]),
     "gs_mark_visible": (C.c_int, [C.c_int32, _vp, _vp, _vp, _vp]),

@@ -99,6 +99,11 @@ static int run_front(const GsProblem* p, const GsParams& q, const GsLayout& L, i
 
 extern "C" int gs_forward(const GsProblem* p, const GsForwardOut* out, gs_stream_t stream)
 {
+    return gs_forward_stages(p, out, GS_FWD_ALL, stream);
+}
+
+extern "C" int gs_forward_stages(const GsProblem* p, const GsForwardOut* out, uint32_t stages, gs_stream_t stream)
+{
     int r = validate(p);
     if (r) return r;
     if (!out || !out->color || !out->depth || !out->alpha || (p->N > 0 && !out->radii)) return GS_E_BAD_ARGS;
@@ -116,19 +121,32 @@ extern "C" int gs_forward(const GsProblem* p, const GsForwardOut* out, gs_stream
         CK(cudaMemsetAsync(q.tile_start, 0, 4 * (size_t)(L.total_tiles + 1), s));
         return 0;
     }
-    r = run_front(p, q, L, out->radii, s);
-    if (r) return r;
-    gs_launch_scatter(q, out->radii, s);
-    CK_LAUNCH("scatter_kernel");
+    if (stages & GS_FWD_PREPROCESS) {
+        r = run_front(p, q, L, out->radii, s);
+        if (r) return r;
+    }
+    if (stages & GS_FWD_SCATTER) {
+        gs_launch_scatter(q, out->radii, s);
+        CK_LAUNCH("scatter_kernel");
+    }
     const int sms = sm_count();
-    gs_launch_sort_gather(q, sms, s);
-    CK_LAUNCH("sort_gather_kernel");
-    gs_launch_blend_fwd(q, out->color, out->depth, out->alpha, sms, s);
-    CK_LAUNCH("blend_fwd_kernel");
+    if (stages & GS_FWD_SORT) {
+        gs_launch_sort_gather(q, sms, s);
+        CK_LAUNCH("sort_gather_kernel");
+    }
+    if (stages & GS_FWD_BLEND) {
+        gs_launch_blend_fwd(q, out->color, out->depth, out->alpha, sms, s);
+        CK_LAUNCH("blend_fwd_kernel");
+    }
     return 0;
 }
 
 extern "C" int gs_backward(const GsProblem* p, const GsBackwardIO* io, gs_stream_t stream)
+{
+    return gs_backward_stages(p, io, GS_BWD_ALL, stream);
+}
+
+extern "C" int gs_backward_stages(const GsProblem* p, const GsBackwardIO* io, uint32_t stages, gs_stream_t stream)
 {
     int r = validate(p);
     if (r) return r;
@@ -140,11 +158,15 @@ extern "C" int gs_backward(const GsProblem* p, const GsBackwardIO* io, gs_stream
     cudaStream_t s = (cudaStream_t)stream;
     const GsLayout L = gs_make_layout(p->N, p->V, p->H, p->W, p->cap_instances);
     const GsParams q = make_params(p, L);
-    CK(cudaMemsetAsync(q.grad2d, 0, 48 * (size_t)p->V * p->N, s));
-    gs_launch_blend_bwd(q, io->dL_dcolor, io->dL_ddepth, io->dL_dalpha, sm_count(), s);
-    CK_LAUNCH("blend_bwd_kernel");
-    gs_launch_preprocess_bwd(q, *io, s);
-    CK_LAUNCH("preprocess_bwd_kernel");
+    if (stages & GS_BWD_BLEND) {
+        CK(cudaMemsetAsync(q.grad2d, 0, 48 * (size_t)p->V * p->N, s));
+        gs_launch_blend_bwd(q, io->dL_dcolor, io->dL_ddepth, io->dL_dalpha, sm_count(), s);
+        CK_LAUNCH("blend_bwd_kernel");
+    }
+    if (stages & GS_BWD_PREPROCESS) {
+        gs_launch_preprocess_bwd(q, *io, s);
+        CK_LAUNCH("preprocess_bwd_kernel");
+    }
     return 0;
 }
 
@@ -172,9 +194,7 @@ extern "C" int gs_count_instances(const GsProblem* p, int64_t* n_host, gs_stream
     cudaStream_t s = (cudaStream_t)stream;
     const GsLayout L = gs_make_layout(p->N, p->V, p->H, p->W, p->cap_instances);
     const GsParams q = make_params(p, L);
-    // radii scratch: the geometry record area is not needed yet by anyone else, but radii is an
-    // output of forward; here we borrow the n_contrib area (>= V*N ints is NOT guaranteed), so use sorted_ids
-    // only if it is large enough -- otherwise the clamped/geom area.  Simplest safe choice: grad2d (48*V*N bytes).
+    // radii is an output of the real forward; this counting pass borrows the grad2d area (48*V*N bytes) for it
     int32_t* radii = (int32_t*)q.grad2d;
     r = run_front(p, q, L, radii, s);
     if (r) return r;

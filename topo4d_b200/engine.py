@@ -15,6 +15,12 @@ import torch
 from . import _lib
 from ._lib import GS_CAM_FLOATS, GsBackwardIO, GsForwardOut, GsProblem, GsStatus, GsWorkspaceView
 
+FWD_STAGES = (("preprocess", _lib.GS_FWD_PREPROCESS), ("scatter", _lib.GS_FWD_SCATTER), ("sort_gather", _lib.GS_FWD_SORT),
+              ("blend_fwd", _lib.GS_FWD_BLEND))
+BWD_STAGES = (("blend_bwd", _lib.GS_BWD_BLEND), ("preprocess_bwd", _lib.GS_BWD_PREPROCESS))
+# kernels launched by one forward / one backward call (memsets are not kernels)
+KERNELS_PER_FORWARD, KERNELS_PER_BACKWARD = 6, 2
+
 # remembered instance capacity per problem shape (grown on overflow)
 _CAP_MEMO: dict[tuple, int] = {}
 
@@ -107,12 +113,15 @@ def _check_pairs(shs, colors_precomp, scales, rotations, cov3D_precomp):
 
 def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None, colors_precomp=None,
             scales=None, rotations=None, cov3D_precomp=None, sh_degree=0, scale_modifier=1.0, debug=False,
-            check="sync", cap_instances=None):
+            check="sync", cap_instances=None, stage_events=None):
     """Render V views.  `cameras`: [V,48] float32 CUDA tensor (see include/topo4d_b200.h GS_CAM_*).
 
     check: "sync"  -> read the status block after the launch (one small D2H, like upstream's
                       num_rendered read) and transparently re-run with a larger capacity on overflow;
            "none"  -> fully asynchronous; call ``state.status()`` later to validate.
+    stage_events: optional dict; when given, the pipeline is issued one stage at a time
+           (gs_forward_stages) with CUDA events recorded around every stage on the current stream
+           and appended to stage_events[stage_name] as (start, end) pairs.
     Returns (color[V,3,H,W], radii[V,N] i32, depth[V,1,H,W], alpha[V,1,H,W], RasterState)."""
     _check_pairs(shs, colors_precomp, scales, rotations, cov3D_precomp)
     if not means3D.is_cuda:
@@ -157,7 +166,15 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
             cap = int(n.value * 1.25) + 4096
         while True:
             pr, ws = make_problem(cap)
-            _lib.check(L.gs_forward(C.byref(pr), C.byref(out), stream), "gs_forward")
+            if stage_events is None:
+                _lib.check(L.gs_forward(C.byref(pr), C.byref(out), stream), "gs_forward")
+            else:
+                for name, bit in FWD_STAGES:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    _lib.check(L.gs_forward_stages(C.byref(pr), C.byref(out), bit, stream), "gs_forward_stages:" + name)
+                    e1.record()
+                    stage_events.setdefault(name, []).append((e0, e1))
             state = RasterState(pr, ws, (means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, cameras),
                                 radii, N, V, H, W, M, shs is not None, cov3D_precomp is not None, dev)
             if check != "sync":
@@ -190,7 +207,8 @@ def _al4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
-def backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None, flat: torch.Tensor | None = None) -> GradBundle:
+def backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None, flat: torch.Tensor | None = None,
+             stage_events=None) -> GradBundle:
     """Gradients summed over the V views of `state`.  dL_dcolor [V,3,H,W] (or [3,H,W] when V == 1)."""
     L = _lib.lib()
     dev, N, V, H, W, M = state.device, state.N, state.V, state.H, state.W, state.M
@@ -220,8 +238,16 @@ def backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None, flat
                       _ptr(seg["a"]) if state.use_cov else None)
     if N > 0:
         with torch.cuda.device(dev):
-            _lib.check(L.gs_backward(C.byref(state.problem), C.byref(io),
-                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "gs_backward")
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if stage_events is None:
+                _lib.check(L.gs_backward(C.byref(state.problem), C.byref(io), stream), "gs_backward")
+            else:
+                for name, bit in BWD_STAGES:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    _lib.check(L.gs_backward_stages(C.byref(state.problem), C.byref(io), bit, stream), "gs_backward_stages:" + name)
+                    e1.record()
+                    stage_events.setdefault(name, []).append((e0, e1))
     g = GradBundle(flat=flat, means3D=seg["means3D"].view(N, 3), means2D=seg["means2D"].view(N, 3),
                    opacities=seg["opacities"].view(N, 1))
     if state.use_sh:

@@ -1,0 +1,27 @@
+"""View-parallel data parallelism: one process per GPU, every rank holds a full replica
+of the Gaussians and renders views {r, r+G, ...}; one all-reduce (sum) of the flat gradient buffer per
+optimiser step over NCCL / NVLink.  The reference has no distributed code (train.py renders one view
+per Adam step in one process); this is the only collective on the path and it is a real exchange step.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views: int, rank: int, world: int) -> list[int]:
+    """Round-robin ownership: rank r renders views r, r+world, ... (24 views divide by 1/2/4/8)."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    return list(range(rank, n_views, world))
+
+
+def allreduce_flat_(flat: torch.Tensor, average: bool = False) -> torch.Tensor:
+    """In-place sum (or mean) of the contiguous fp32 gradient buffer across ranks: ONE collective call."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return flat
+    assert flat.is_contiguous()
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if average:
+        flat.div_(dist.get_world_size())
+    return flat
