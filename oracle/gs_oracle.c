@@ -410,48 +410,55 @@ static void blend_tile_bwd(const GsoState* s, int tile, const float* gC, const f
         const float g_c[3] = {gC[pix], gC[HW + pix], gC[2*HW + pix]};
         const float g_d = gD[pix], g_a = gA[pix];
         const float bg_dot = s->bg[0]*g_c[0] + s->bg[1]*g_c[1] + s->bg[2]*g_c[2];
-        float T = T_final;
-        float rec_c[3] = {0, 0, 0}, rec_d = 0, rec_a = 0;
-        float last_alpha = 0, last_c[3] = {0, 0, 0}, last_d = 0;
+        /* Which Gaussians take part is decided exactly as the fp32 forward decided it (float power /
+         * alpha tests, n_contrib); the VALUES of the replay are carried in double so that the oracle is
+         * the accurate gradient of that forward and not one more fp32 rounding of it (the T = T/(1-alpha)
+         * recovery amplifies fp32 noise by alpha/(1-alpha) per layer, up to 100x at the 0.99 cap). */
+        double T = (double)T_final;
+        double rec_c[3] = {0, 0, 0}, rec_d = 0, rec_a = 0;
+        double last_alpha = 0, last_c[3] = {0, 0, 0}, last_d = 0;
         for (int64_t k = (int64_t)beg + last - 1; k >= (int64_t)beg; k--) {
             const uint32_t g = s->vals[k];
-            const float dx = s->xy[2*g] - pxf, dy = s->xy[2*g+1] - pyf;
+            const float dxf = s->xy[2*g] - pxf, dyf = s->xy[2*g+1] - pyf;
             const float* co = s->conic_o + 4*g;
-            const float power = -0.5f * (co[0]*dx*dx + co[2]*dy*dy) - co[1]*dx*dy;
-            if (power > 0.0f) continue;
-            const float G = expf(power);
-            const float alpha = fminf_(ALPHA_CAP, co[3] * G);
-            if (alpha < ALPHA_MIN) continue;
-            T = T / (1.0f - alpha);
-            const float w = alpha * T;
+            const float power_f = -0.5f * (co[0]*dxf*dxf + co[2]*dyf*dyf) - co[1]*dxf*dyf;
+            if (power_f > 0.0f) continue;
+            const float alpha_f = fminf_(ALPHA_CAP, co[3] * expf(power_f));
+            if (alpha_f < ALPHA_MIN) continue;
+            const double dx = (double)s->xy[2*g] - (double)pxf, dy = (double)s->xy[2*g+1] - (double)pyf;
+            const double cA = co[0], cB = co[1], cC = co[2], op = co[3];
+            const double G = exp(-0.5 * (cA*dx*dx + cC*dy*dy) - cB*dx*dy);
+            const double alpha = fmin((double)ALPHA_CAP, op * G);
+            T = T / (1.0 - alpha);
+            const double w = alpha * T;
             double* a = acc + (size_t)g * 10;
-            float dL_dalpha = 0.0f;
+            double dL_dalpha = 0.0;
             for (int ch = 0; ch < 3; ch++) {
-                const float c = s->rgb[3*g+ch];
-                rec_c[ch] = last_alpha * last_c[ch] + (1.0f - last_alpha) * rec_c[ch];
+                const double c = s->rgb[3*g+ch];
+                rec_c[ch] = last_alpha * last_c[ch] + (1.0 - last_alpha) * rec_c[ch];
                 last_c[ch] = c;
                 dL_dalpha += (c - rec_c[ch]) * g_c[ch];
-                a[6+ch] += (double)(w * g_c[ch]);
+                a[6+ch] += w * g_c[ch];
             }
-            const float dep = s->depth[g];
-            rec_d = last_alpha * last_d + (1.0f - last_alpha) * rec_d;
+            const double dep = s->depth[g];
+            rec_d = last_alpha * last_d + (1.0 - last_alpha) * rec_d;
             last_d = dep;
             dL_dalpha += (dep - rec_d) * g_d;
-            a[9] += (double)(w * g_d);
-            rec_a = last_alpha + (1.0f - last_alpha) * rec_a;
-            dL_dalpha += (1.0f - rec_a) * g_a;
+            a[9] += w * g_d;
+            rec_a = last_alpha + (1.0 - last_alpha) * rec_a;
+            dL_dalpha += (1.0 - rec_a) * g_a;
             dL_dalpha *= T;
             last_alpha = alpha;
-            dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+            dL_dalpha += (-(double)T_final / (1.0 - alpha)) * bg_dot;
             /* straight-through the 0.99 cap (A.7): no clamp mask */
-            const float dL_dG = co[3] * dL_dalpha;
-            const float gdx = G * dx, gdy = G * dy;
-            a[0] += (double)(dL_dG * (-gdx * co[0] - gdy * co[1]));
-            a[1] += (double)(dL_dG * (-gdy * co[2] - gdx * co[1]));
-            a[2] += (double)(-0.5f * gdx * dx * dL_dG);
-            a[3] += (double)(-gdx * dy * dL_dG);
-            a[4] += (double)(-0.5f * gdy * dy * dL_dG);
-            a[5] += (double)(G * dL_dalpha);
+            const double dL_dG = op * dL_dalpha;
+            const double gdx = G * dx, gdy = G * dy;
+            a[0] += dL_dG * (-gdx * cA - gdy * cB);
+            a[1] += dL_dG * (-gdy * cC - gdx * cB);
+            a[2] += -0.5 * gdx * dx * dL_dG;
+            a[3] += -gdx * dy * dL_dG;
+            a[4] += -0.5 * gdy * dy * dL_dG;
+            a[5] += G * dL_dalpha;
         }
     }
 }

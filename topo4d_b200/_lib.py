@@ -77,8 +77,8 @@ def lib():
     """Load (building in-tree if stale/missing) the CUDA library.  Raises if that is impossible."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB_PATH
-        if not os.path.exists(path) or os.environ.get("TOPO4D_B200_REBUILD") == "1":
+        path = os.environ.get("TOPO4D_B200_LIB") or _build.LIB_PATH      # override: experiment variants (build.py --tag)
+        if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("TOPO4D_B200_REBUILD") == "1"):
             path = _build.build_library()
         handle = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():

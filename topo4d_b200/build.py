@@ -1,9 +1,10 @@
 """In-tree build of libtopo4d_b200.so with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m topo4d_b200.build          # or  __graft_entry__.build()
+    python -m topo4d_b200.build [-v] [--force] [--tag NAME -DFOO=1 ...]
 
 The library lands in ``topo4d_b200/_build/`` (git-ignored, shipped to the GPU box by gpurun).
-Rebuilds only when a source is newer than the library.
+Rebuilds only when a source is newer than the library.  ``--tag`` builds an experiment variant
+``libtopo4d_b200_<tag>.so`` with extra -D defines (selected at run time with TOPO4D_B200_LIB=<path>).
 """
 from __future__ import annotations
 
@@ -38,24 +39,26 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+def _stale(lib_path: str) -> bool:
+    if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(lib_path)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "topo4d_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB_PATH
-    os.makedirs(OUT_DIR, exist_ok=True)
+def build_library(force: bool = False, verbose: bool = False, tag: str = "", defines: list[str] | None = None) -> str:
+    lib_path = LIB_PATH if not tag else os.path.join(OUT_DIR, f"libtopo4d_b200_{tag}.so")
+    if not force and not _stale(lib_path):
+        return lib_path
+    obj_dir = OUT_DIR if not tag else os.path.join(OUT_DIR, tag)
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     objs = []
     procs = []
     for src, extra in SOURCES:
-        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *(defines or []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
@@ -67,12 +70,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             print(out, file=sys.stderr)
         if pr.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    link = [nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs]
+    link = [nvcc, *ARCH, "-shared", "-o", lib_path, *objs]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    argv = sys.argv[1:]
+    tag = argv[argv.index("--tag") + 1] if "--tag" in argv else ""
+    print(build_library(force="--force" in argv, verbose="-v" in argv, tag=tag,
+                        defines=[x for x in argv if x.startswith("-D")]))

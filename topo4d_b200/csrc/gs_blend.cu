@@ -32,6 +32,19 @@ __device__ __forceinline__ float splat_power(float cA, float cB, float cC, float
     return __fmaf_rn(-0.5f, t2, -t3);
 }
 __device__ __forceinline__ float splat_alpha(float opacity, float G) { return fminf(GS_ALPHA_CAP, __fmul_rn(opacity, G)); }
+// exp flavour: GS_PRECISE_EXP=1 -> expf (~1 ulp, what upstream's exp() compiles to);
+//              default          -> __expf (ex2.approx of x*log2e; ~2+|1.17x| ulp, 2 instructions)
+#ifndef GS_PRECISE_EXP
+#define GS_PRECISE_EXP 0
+#endif
+__device__ __forceinline__ float splat_exp(float power)
+{
+#if GS_PRECISE_EXP
+    return expf(power);
+#else
+    return __expf(power);
+#endif
+}
 
 struct TileCtx {
     int v, px, py;
@@ -99,7 +112,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
                     const float dx = r0.x - pxf, dy = r0.y - pyf;
                     const float power = splat_power(r0.z, r0.w, r1.x, dx, dy);
                     if (power > 0.0f) continue;
-                    const float alpha = splat_alpha(r1.y, __expf(power));
+                    const float alpha = splat_alpha(r1.y, splat_exp(power));
                     if (alpha < GS_ALPHA_MIN) continue;
                     const float test_T = T * (1.0f - alpha);
                     if (test_T < GS_T_MIN) { done = true; break; }
@@ -214,7 +227,7 @@ blend_bwd_kernel(const GsParams p, const float* __restrict__ g_color, const floa
                 const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
                 const float dx = r0.x - pxf, dy = r0.y - pyf;
                 const float power = splat_power(r0.z, r0.w, r1.x, dx, dy);
-                const float G = __expf(power);
+                const float G = splat_exp(power);
                 const float alpha = splat_alpha(r1.y, G);
                 const bool contrib = (idx < last) && (power <= 0.0f) && (alpha >= GS_ALPHA_MIN);
                 if (!__any_sync(0xffffffffu, contrib)) continue;
