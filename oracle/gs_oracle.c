@@ -392,6 +392,70 @@ void gso_get_image_state(const GsoState* s, float* final_T, uint32_t* n_contrib)
     if (n_contrib) memcpy(n_contrib, s->n_contrib, HW*4);
 }
 
+/* --- A.6 backward blend of one tile, REFERENCE-FAITHFUL fp32 replay (every value a float, as the CUDA
+ *     reference computes it; only the cross-pixel accumulation is double).  Used to measure how far the fp32
+ *     algorithm itself sits from the accurate gradient (blend_tile_bwd below), i.e. the noise floor any fp32
+ *     implementation of this path has in ill-conditioned regimes (alpha at the 0.99 cap). */
+static void blend_tile_bwd_f32(const GsoState* s, int tile, const float* gC, const float* gD, const float* gA, double* acc)
+{
+    const int tx0 = (tile % s->gx) * TILE, ty0 = (tile / s->gx) * TILE;
+    const uint32_t beg = s->ranges[2*tile];
+    const size_t HW = (size_t)s->H * s->W;
+    for (int ly = 0; ly < TILE; ly++) for (int lx = 0; lx < TILE; lx++) {
+        const int x = tx0 + lx, y = ty0 + ly;
+        if (x >= s->W || y >= s->H) continue;
+        const size_t pix = (size_t)y * s->W + x;
+        const float pxf = (float)x, pyf = (float)y;
+        const float T_final = s->final_T[pix];
+        const uint32_t last = s->n_contrib[pix];
+        const float g_c[3] = {gC[pix], gC[HW + pix], gC[2*HW + pix]};
+        const float g_d = gD[pix], g_a = gA[pix];
+        const float bg_dot = s->bg[0]*g_c[0] + s->bg[1]*g_c[1] + s->bg[2]*g_c[2];
+        float T = T_final;
+        float rec_c[3] = {0, 0, 0}, rec_d = 0, rec_a = 0;
+        float last_alpha = 0, last_c[3] = {0, 0, 0}, last_d = 0;
+        for (int64_t k = (int64_t)beg + last - 1; k >= (int64_t)beg; k--) {
+            const uint32_t g = s->vals[k];
+            const float dx = s->xy[2*g] - pxf, dy = s->xy[2*g+1] - pyf;
+            const float* co = s->conic_o + 4*g;
+            const float power = -0.5f * (co[0]*dx*dx + co[2]*dy*dy) - co[1]*dx*dy;
+            if (power > 0.0f) continue;
+            const float G = expf(power);
+            const float alpha = fminf_(ALPHA_CAP, co[3] * G);
+            if (alpha < ALPHA_MIN) continue;
+            T = T / (1.0f - alpha);
+            const float w = alpha * T;
+            double* a = acc + (size_t)g * 10;
+            float dL_dalpha = 0.0f;
+            for (int ch = 0; ch < 3; ch++) {
+                const float c = s->rgb[3*g+ch];
+                rec_c[ch] = last_alpha * last_c[ch] + (1.0f - last_alpha) * rec_c[ch];
+                last_c[ch] = c;
+                dL_dalpha += (c - rec_c[ch]) * g_c[ch];
+                a[6+ch] += (double)(w * g_c[ch]);
+            }
+            const float dep = s->depth[g];
+            rec_d = last_alpha * last_d + (1.0f - last_alpha) * rec_d;
+            last_d = dep;
+            dL_dalpha += (dep - rec_d) * g_d;
+            a[9] += (double)(w * g_d);
+            rec_a = last_alpha + (1.0f - last_alpha) * rec_a;
+            dL_dalpha += (1.0f - rec_a) * g_a;
+            dL_dalpha *= T;
+            last_alpha = alpha;
+            dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+            const float dL_dG = co[3] * dL_dalpha;
+            const float gdx = G * dx, gdy = G * dy;
+            a[0] += (double)(dL_dG * (-gdx * co[0] - gdy * co[1]));
+            a[1] += (double)(dL_dG * (-gdy * co[2] - gdx * co[1]));
+            a[2] += (double)(-0.5f * gdx * dx * dL_dG);
+            a[3] += (double)(-gdx * dy * dL_dG);
+            a[4] += (double)(-0.5f * gdy * dy * dL_dG);
+            a[5] += (double)(G * dL_dalpha);
+        }
+    }
+}
+
 /* --- A.6 backward blend of one tile into per-thread double accumulators acc[N][10]:
  *     0,1: dL/dpix (pixel units)  2,3,4: dL/d(conic A, B(true), C)  5: dL/dopacity
  *     6,7,8: dL/drgb  9: dL/ddepth */
@@ -610,10 +674,11 @@ static void preprocess_bwd_one(const GsoState* s, int i, const double* a,
  * Outputs are ACCUMULATED INTO (caller zero-fills): means3D [N,3], means2D [N,3] (NDC-scaled, z=0),
  * shs [N,M,3] or colors [N,3], opacities [N], scales [N,3], rotations [N,4] (or cov3D [N,6]).
  * Optional raw 2D accumulators out (acc2d [N,10], see blend_tile_bwd) for stage-wise checks.
+ * f32_replay != 0 selects the reference-faithful fp32 blend replay (noise-floor measurement).
  */
 void gso_backward(const GsoState* s, const float* g_color, const float* g_depth, const float* g_alpha,
                   float* g_means3D, float* g_means2D, float* g_shs, float* g_colors, float* g_opac,
-                  float* g_scales, float* g_rots, float* g_cov3D, double* acc2d_out)
+                  float* g_scales, float* g_rots, float* g_cov3D, double* acc2d_out, int f32_replay)
 {
     const int N = s->N, tiles = s->gx * s->gy;
     if (N == 0) return;
@@ -630,7 +695,10 @@ void gso_backward(const GsoState* s, const float* g_color, const float* g_depth,
 #endif
         double* acc = accs + (size_t)tid * N * 10;
         #pragma omp for schedule(dynamic, 4)
-        for (int t = 0; t < tiles; t++) blend_tile_bwd(s, t, g_color, g_depth, g_alpha, acc);
+        for (int t = 0; t < tiles; t++) {
+            if (f32_replay) blend_tile_bwd_f32(s, t, g_color, g_depth, g_alpha, acc);
+            else blend_tile_bwd(s, t, g_color, g_depth, g_alpha, acc);
+        }
     }
     for (int t = 1; t < nth; t++) {
         const double* src = accs + (size_t)t * N * 10;

@@ -24,7 +24,7 @@ def _L():
         lib.gso_get_geometry.argtypes = [C.c_void_p] + [fp] * 8
         lib.gso_get_binning.argtypes = [C.c_void_p] + [fp] * 3
         lib.gso_get_image_state.argtypes = [C.c_void_p] + [fp] * 2
-        lib.gso_backward.argtypes = [C.c_void_p] + [fp] * 12
+        lib.gso_backward.argtypes = [C.c_void_p] + [fp] * 12 + [C.c_int]
         lib.gso_mark_visible.argtypes = [C.c_int, fp, fp, fp]
         lib.gso_num_threads.restype = C.c_int
         _lib = lib
@@ -87,7 +87,7 @@ class GsOracleState:
         _L().gso_get_image_state(self._h, _p(final_T), _p(n_contrib))
         return dict(final_T=final_T, n_contrib=n_contrib)
 
-    def backward(self, g_color, g_depth=None, g_alpha=None, return_acc2d=False):
+    def backward(self, g_color, g_depth=None, g_alpha=None, return_acc2d=False, f32_replay=False):
         H, W, N, M = self.H, self.W, self.N, self.M
         g_color = _f32(g_color).reshape(3, H, W)
         g_depth = np.zeros((H, W), np.float32) if g_depth is None else _f32(g_depth).reshape(H, W)
@@ -99,7 +99,7 @@ class GsOracleState:
         acc = np.zeros((max(N, 1), 10), np.float64) if return_acc2d else None
         _L().gso_backward(self._h, _p(g_color), _p(g_depth), _p(g_alpha),
                           _p(g["means3D"]), _p(g["means2D"]), _p(g["shs"]), _p(g["colors_precomp"]), _p(g["opacities"]),
-                          _p(g["scales"]), _p(g["rotations"]), _p(g["cov3D_precomp"]), _p(acc))
+                          _p(g["scales"]), _p(g["rotations"]), _p(g["cov3D_precomp"]), _p(acc), int(bool(f32_replay)))
         if not self.use_sh:
             g.pop("shs")
         else:

@@ -25,7 +25,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 SOURCES = [
     ("gs_preprocess.cu", ["--fmad=false"]),
     ("gs_binning.cu", []),
-    ("gs_blend.cu", []),
+    ("gs_blend.cu", ["-DGS_PRECISE_EXP=1"]),   # expf (<= 1 ulp) on the blended pairs; =0 selects ex2.approx
     ("gs_backward.cu", []),
     ("gs_api.cu", []),
     ("f3d_render.cu", ["--fmad=false"]),
@@ -43,7 +43,8 @@ def _stale(lib_path: str) -> bool:
     if not os.path.exists(lib_path):
         return True
     t = os.path.getmtime(lib_path)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "topo4d_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "topo4d_b200.h"),
+                                                                os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -35,6 +35,7 @@ static int validate(const GsProblem* p)
     if (p->N < 0 || p->V < 1 || p->H < 1 || p->W < 1) return GS_E_BAD_ARGS;
     if (p->cap_instances < 0 || p->cap_instances > 0x7fffffffLL) return GS_E_BAD_ARGS;
     if ((long long)p->V * p->N > 0x7fffffffLL) return GS_E_BAD_ARGS;
+    if ((long long)p->V * ((p->W + GS_TILE - 1) / GS_TILE) * ((p->H + GS_TILE - 1) / GS_TILE) > 0x7fffffffLL) return GS_E_BAD_ARGS;
     if (!p->workspace || !p->cameras) return GS_E_BAD_ARGS;
     if (p->N > 0) {
         if (!p->means3D || !p->opacities) return GS_E_BAD_ARGS;
@@ -66,6 +67,7 @@ static GsParams make_params(const GsProblem* p, const GsLayout& L)
     q.tile_count = (uint32_t*)(ws + L.off_tile_count);
     q.tile_start = (uint32_t*)(ws + L.off_tile_start);
     q.tile_fill = (uint32_t*)(ws + L.off_tile_fill);
+    q.active_tiles = (uint32_t*)(ws + L.off_active);
     q.block_sums = (uint32_t*)(ws + L.off_block_sums);
     q.clamped = (uint8_t*)(ws + L.off_clamped);
     q.geom = (float4*)(ws + L.off_geom);
@@ -135,6 +137,7 @@ extern "C" int gs_forward_stages(const GsProblem* p, const GsForwardOut* out, ui
         CK_LAUNCH("sort_gather_kernel");
     }
     if (stages & GS_FWD_BLEND) {
+        CK(cudaMemsetAsync(&q.status->q_fwd_heavy, 0, 2 * sizeof(unsigned int), s));     // both forward queues
         gs_launch_blend_fwd(q, out->color, out->depth, out->alpha, sms, s);
         CK_LAUNCH("blend_fwd_kernel");
     }
@@ -159,8 +162,9 @@ extern "C" int gs_backward_stages(const GsProblem* p, const GsBackwardIO* io, ui
     const GsLayout L = gs_make_layout(p->N, p->V, p->H, p->W, p->cap_instances);
     const GsParams q = make_params(p, L);
     if (stages & GS_BWD_BLEND) {
+        CK(cudaMemsetAsync(&q.status->q_bwd_heavy, 0, sizeof(unsigned int), s));
         CK(cudaMemsetAsync(q.grad2d, 0, 48 * (size_t)p->V * p->N, s));
-        gs_launch_blend_bwd(q, io->dL_dcolor, io->dL_ddepth, io->dL_dalpha, sm_count(), s);
+        gs_launch_blend_bwd(q, *io, sm_count(), s);
         CK_LAUNCH("blend_bwd_kernel");
     }
     if (stages & GS_BWD_PREPROCESS) {

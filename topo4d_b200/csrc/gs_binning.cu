@@ -95,12 +95,32 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const GsParams
     if (w == 0) { uint32_t x = s_warp[lane]; x = warp_incl_scan(x, lane); s_warp[lane] = x; }
     __syncthreads();
     unsigned long long run = pre + (w > 0 ? s_warp[w - 1] : 0u) + (incl - tsum);
+    uint32_t nact = 0;
     #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         const long long e = base + k;
         if (e <= n) p.tile_start[e] = (uint32_t)(run > 0xffffffffull ? 0xffffffffull : run);
         if (e < n) p.tile_fill[e] = 0u;
+        if (e < n && c[k] > 0u) nact++;
         run += c[k];
+    }
+    // compact the non-empty tiles into active_tiles[] (one atomic per block; order across blocks is arbitrary,
+    // which only changes the order tiles are worked on, never a result)
+    __shared__ uint32_t s_awarp[32];
+    __shared__ uint32_t s_abase;
+    const uint32_t aincl = warp_incl_scan(nact, lane);
+    __syncthreads();
+    if (lane == 31) s_awarp[w] = aincl;
+    __syncthreads();
+    if (w == 0) { uint32_t x = s_awarp[lane]; x = warp_incl_scan(x, lane); s_awarp[lane] = x; }
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1) s_abase = atomicAdd(&p.status->num_active, s_awarp[31]);
+    __syncthreads();
+    uint32_t apos = s_abase + (w > 0 ? s_awarp[w - 1] : 0u) + (aincl - nact);
+    #pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const long long e = base + k;
+        if (e < n && c[k] > 0u) p.active_tiles[apos++] = (uint32_t)e;
     }
     if (base <= n && n < base + SCAN_ITEMS) {   // the thread that owns element n holds the grand total
         unsigned long long total = pre + (w > 0 ? s_warp[w - 1] : 0u) + (incl - tsum);

@@ -2,65 +2,99 @@
 //
 // Replaces upstream renderCUDA forward/backward of the un-vendored rasterizer behind
 // GaussianRasterizer (reference call sites train.py:307,388 forward; train.py:667,738 backward).
-// Same per-pixel arithmetic (alpha = min(0.99, o*exp(power)), skip alpha<1/255,
-// stop at T(1-alpha)<1e-4, straight-through cap in backward), different machine mapping:
-//   * persistent CTAs walk (view, tile) pairs; a CTA owns one 16x16 binning tile at a time, each of
-//     its 8 warps an 8x4-pixel block (32-byte row segments per plane);
-//   * the tile's depth-sorted 48-byte records are contiguous in HBM (gs_binning.cu), so a chunk of
-//     128 records is ONE cp.async.bulk (SASS UBLKCP) into shared memory, double-buffered on two
-//     mbarriers: no per-thread gather, no register staging;
-//   * forward: a warp leaves the chunk loop as soon as all 32 of its pixels are saturated;
-//   * backward: starts at the tile's deepest contributor (block-max n_contrib), skips records no
-//     pixel of the warp touches (ballot), reduces the 10 per-Gaussian partials across the warp with a
-//     halving butterfly (16 shuffles instead of 50), accumulates the 8 warps in shared memory and
-//     issues three 16-byte vector REDs per (tile, Gaussian) instead of 10 scalar atomics per pixel.
+// Same per-pixel semantics (alpha = min(0.99, o*exp(power)), skip alpha < 1/255,
+// stop at T(1-alpha) < 1e-4, straight-through cap in backward); the machine mapping is new:
+//
+//   * work = (view, 16x16 binning tile).  Persistent 64-thread CTAs pull tiles from device-side queues
+//     (atomic counters in the status block): the compacted list of NON-EMPTY tiles, and -- forward only --
+//     groups of 16 tiles whose empty members just receive the background.  Even CTAs start on the heavy
+//     queue, odd CTAs on the fill queue, so the issue-bound blending and the HBM-bound background stream
+//     overlap on every SM and nobody idles on a static tile->CTA map.
+//   * a thread owns a vertical comb of 4 pixels (x, y+4k): lane (lx,ly) of warp w sits at column 8w+lx,
+//     rows ly+4k.  The column terms of the quadratic form are shared by the 4 pixels (3 FP ops per pixel
+//     for `power`), and pixel slot k of a warp is one COMPACT 8x4 block, so the divergent blend code of a
+//     slot runs only when the splat reaches that block and with a dense lane mask.
+//   * a conservative per-Gaussian threshold `thr` (stored in the record) rejects a pixel without touching
+//     exp(); ~88 % of (pixel, Gaussian) pairs leave after 5 instructions.
+//   * the tile's depth-sorted 48-byte records are contiguous in HBM (gs_binning.cu): a chunk of 64
+//     records is ONE cp.async.bulk (SASS UBLKCP) into shared memory, double-buffered on two mbarriers.
+//   * backward replays back-to-front from the tile's deepest contributor with T_i = T_{i+1}/(1-alpha_i).
+//     alpha is re-derived by the SAME inlined code as in the forward (identical bits), so the division
+//     undoes the forward's multiplication to within ulps and nothing is amplified by 1/(1-alpha); the
+//     colour/depth/alpha "behind" terms are plain suffix sums built from the back (small terms first).
+//     The 10 per-Gaussian partials are pre-added over a thread's 4 pixels, reduced across the warp with a
+//     halving butterfly (16 shuffles instead of 50), parked in a per-warp shared-memory slot (no atomics)
+//     and flushed with three 16-byte vector REDs per (tile, Gaussian).
 #include "gs_common.cuh"
 
 namespace {
 
-constexpr int BLEND_THREADS = 256;
-constexpr int CHUNK = 128;                    // records per bulk copy (6 KB)
+constexpr int BT = 64;                        // threads per CTA = 2 warps, each an 8-column half of the tile
+constexpr int PX = 4;                         // pixels per thread
+constexpr int CHUNK = 64;                     // records per bulk copy (3 KB)
 constexpr uint32_t REC_BYTES = 48;
+constexpr float LOG2E = 1.4426950408889634f;
 
-// Identical bits in forward and backward: the backward pass must re-derive exactly the alpha the
-// forward pass blended, so the contraction pattern is pinned with explicit intrinsics.
-__device__ __forceinline__ float splat_power(float cA, float cB, float cC, float dx, float dy)
+// ---- per-pair arithmetic shared by forward and backward (identical bits in both) ----
+struct ColTerms { float hC, u, v; };          // power(dy) = dy*(hC*dy + u) + v for a fixed pixel column
+__device__ __forceinline__ ColTerms col_terms(float cA, float cB, float cC, float dx)
 {
-    const float t1 = __fmul_rn(__fmul_rn(cA, dx), dx);
-    const float t2 = __fmaf_rn(__fmul_rn(cC, dy), dy, t1);
-    const float t3 = __fmul_rn(__fmul_rn(cB, dx), dy);
-    return __fmaf_rn(-0.5f, t2, -t3);
+    ColTerms r;
+    r.hC = __fmul_rn(-0.5f, cC);
+    r.u = -__fmul_rn(cB, dx);
+    r.v = __fmul_rn(__fmul_rn(-0.5f, __fmul_rn(cA, dx)), dx);
+    return r;
 }
-__device__ __forceinline__ float splat_alpha(float opacity, float G) { return fminf(GS_ALPHA_CAP, __fmul_rn(opacity, G)); }
-// exp flavour: GS_PRECISE_EXP=1 -> expf (~1 ulp, what upstream's exp() compiles to);
-//              default          -> __expf (ex2.approx of x*log2e; ~2+|1.17x| ulp, 2 instructions)
-#ifndef GS_PRECISE_EXP
-#define GS_PRECISE_EXP 0
-#endif
+__device__ __forceinline__ float splat_power(const ColTerms& r, float dy)
+{
+    return __fmaf_rn(dy, __fmaf_rn(r.hC, dy, r.u), r.v);
+}
 __device__ __forceinline__ float splat_exp(float power)
 {
-#if GS_PRECISE_EXP
+#if defined(GS_PRECISE_EXP) && GS_PRECISE_EXP
     return expf(power);
 #else
-    return __expf(power);
+    float y = __fmul_rn(power, LOG2E), g;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(y));
+    return g;
 #endif
+}
+__device__ __forceinline__ float splat_alpha(float opacity, float G) { return fminf(GS_ALPHA_CAP, __fmul_rn(opacity, G)); }
+__device__ __forceinline__ float next_T(float T, float alpha) { return __fmul_rn(T, __fsub_rn(1.0f, alpha)); }
+
+// ---- work queues ----
+constexpr long long ITEM_DONE = -1;
+// returns a global tile id (>= 0), a fill group encoded as -(g + 2), or ITEM_DONE
+__device__ __forceinline__ long long fetch_fwd(const GsParams& p, bool prefer_fill, unsigned n_groups)
+{
+    GsStatusDev* st = p.status;
+    const unsigned n_active = st->num_active;
+    #pragma unroll
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const bool fill = (attempt == 0) == prefer_fill;
+        if (fill) {
+            const unsigned g = atomicAdd(&st->q_fwd_fill, 1u);
+            if (g < n_groups) return -((long long)g + 2);
+        } else {
+            const unsigned i = atomicAdd(&st->q_fwd_heavy, 1u);
+            if (i < n_active) return (long long)p.active_tiles[i];
+        }
+    }
+    return ITEM_DONE;
 }
 
 struct TileCtx {
-    int v, px, py;
-    bool inside;
+    int v, tx0, ty0;       // view, first pixel of the tile
     unsigned long long start;
     int n;
 };
-
-__device__ __forceinline__ TileCtx tile_ctx(const GsParams& p, long long tg, int lx, int ly)
+__device__ __forceinline__ TileCtx tile_ctx(const GsParams& p, long long tg)
 {
     TileCtx c;
-    c.v = (int)(tg / p.tiles);
-    const int t = (int)(tg - (long long)c.v * p.tiles);
-    c.px = (t % p.tiles_x) * GS_TILE + lx;
-    c.py = (t / p.tiles_x) * GS_TILE + ly;
-    c.inside = c.px < p.W && c.py < p.H;
+    c.v = (int)((unsigned)tg / (unsigned)p.tiles);            // V*tiles < 2^31 (validated on the host)
+    const int t = (int)tg - c.v * p.tiles;
+    c.tx0 = (t % p.tiles_x) * GS_TILE;
+    c.ty0 = (t / p.tiles_x) * GS_TILE;
     unsigned long long s = p.tile_start[tg], e = p.tile_start[tg + 1];
     if (e > (unsigned long long)p.cap) e = (unsigned long long)p.cap;
     c.start = s;
@@ -68,28 +102,80 @@ __device__ __forceinline__ TileCtx tile_ctx(const GsParams& p, long long tg, int
     return c;
 }
 
-__global__ void __launch_bounds__(BLEND_THREADS)
+// background fill uses a 4x1 strip per thread: one 16-byte store per plane when the row allows it
+__device__ __forceinline__ void store4(float* __restrict__ plane, size_t pix0, float v, int valid, bool vec)
+{
+    if (vec && valid == 4) { *reinterpret_cast<float4*>(plane + pix0) = make_float4(v, v, v, v); return; }
+    #pragma unroll
+    for (int k = 0; k < 4; k++) if (k < valid) plane[pix0 + k] = v;
+}
+
+__global__ void __launch_bounds__(BT)
 blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restrict__ out_depth,
                  float* __restrict__ out_alpha)
 {
     __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cx = warp * 8 + (lane & 7), cy = lane >> 3;          // comb: column cx, rows cy + 4k
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t phases = 0u;                       // bit b = parity to wait for on s_bar[b]
     const size_t HW = (size_t)p.H * p.W;
-    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    const bool vec = (p.W & 3) == 0;
+    const unsigned n_groups = (unsigned)((p.total_tiles + GS_FILL_GROUP - 1) / GS_FILL_GROUP);
+    const bool prefer_fill = blockIdx.x & 1;
 
-    for (long long tg = blockIdx.x; tg < p.total_tiles; tg += gridDim.x) {
-        const TileCtx tc = tile_ctx(p, tg, lx, ly);
-        const float pxf = (float)tc.px, pyf = (float)tc.py;
-        float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, A = 0.f;
-        uint32_t last = 0;
-        bool done = !tc.inside;
+    for (;;) {
+        if (tid == 0) s_item = fetch_fwd(p, prefer_fill, n_groups);
+        __syncthreads();
+        const long long item = s_item;
+        __syncthreads();
+        if (item == ITEM_DONE) break;
+
+        if (item < 0) {
+            // ---- background fill of the empty tiles of one group (thread = 4x1 strip, row tid>>2) ----
+            const long long t0 = (-item - 2) * GS_FILL_GROUP;
+            for (int g = 0; g < GS_FILL_GROUP; g++) {
+                const long long tg = t0 + g;
+                if (tg >= p.total_tiles) break;
+                if (p.tile_start[tg + 1] != p.tile_start[tg]) continue;          // non-empty: a heavy item owns it
+                const TileCtx tc = tile_ctx(p, tg);
+                const int x0 = tc.tx0 + 4 * (tid & 3), y = tc.ty0 + (tid >> 2);
+                const int valid = y < p.H ? min(4, p.W - x0) : 0;
+                if (valid <= 0) continue;
+                const float* __restrict__ bg = p.cams + (size_t)tc.v * GS_CAM_FLOATS + GS_CAM_BG;
+                const size_t vb = (size_t)tc.v * HW, pix0 = (size_t)y * p.W + x0;
+                store4(out_color + vb * 3, pix0, bg[0], valid, vec);
+                store4(out_color + vb * 3 + HW, pix0, bg[1], valid, vec);
+                store4(out_color + vb * 3 + 2 * HW, pix0, bg[2], valid, vec);
+                store4(out_depth + vb, pix0, 0.f, valid, vec);
+                store4(out_alpha + vb, pix0, 0.f, valid, vec);
+                store4(p.final_T + vb, pix0, 1.f, valid, vec);
+                store4(reinterpret_cast<float*>(p.n_contrib) + vb, pix0, 0.f, valid, vec);   // bit pattern 0
+            }
+            continue;
+        }
+
+        // ---- one non-empty tile ----
+        const TileCtx tc = tile_ctx(p, item);
+        const int px = tc.tx0 + cx;
+        const float pxf = (float)px;
+        float pyf[PX], T[PX], C0[PX], C1[PX], C2[PX], D[PX], A[PX];
+        uint32_t last[PX];
+        unsigned done = 0;                                      // bit k: pixel k finished (or outside)
+        #pragma unroll
+        for (int k = 0; k < PX; k++) {
+            const int py = tc.ty0 + cy + 4 * k;
+            pyf[k] = (float)py;
+            T[k] = 1.f; C0[k] = C1[k] = C2[k] = D[k] = A[k] = 0.f; last[k] = 0u;
+            if (px >= p.W || py >= p.H) done |= 1u << k;
+        }
+        const unsigned outside = done;
         const int nchunks = (tc.n + CHUNK - 1) / CHUNK;
         const float4* __restrict__ src = p.sorted_rec + tc.start * 3;
-        if (nchunks > 0 && tid == 0) {
+        if (tid == 0 && nchunks > 0) {
             const uint32_t bytes = (uint32_t)min(tc.n, CHUNK) * REC_BYTES;
             mbar_expect_tx(&s_bar[0], bytes);
             bulk_g2s(s_rec[0], src, bytes, &s_bar[0]);
@@ -105,43 +191,71 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
             mbar_wait(&s_bar[cur], (phases >> cur) & 1u);
             phases ^= 1u << cur;
             const int cnt = min(tc.n - c * CHUNK, CHUNK);
-            if (!__all_sync(0xffffffffu, done)) {
-                const float4* __restrict__ rec = s_rec[cur];
-                for (int j = 0; j < cnt && !done; j++) {
+            const float4* __restrict__ rec = s_rec[cur];
+            // Structured per-record body (no break/continue out of divergent code) closed by __syncwarp(): the
+            // warp re-converges every record.  Leaving the loop from inside the divergent blend block makes the
+            // compiler re-converge only at loop exit, which serialises the 32 lanes (measured: 12x slower).
+            if (!__all_sync(0xffffffffu, done == 0xFu)) {
+                #pragma unroll 2
+                for (int j = 0; j < cnt; j++) {
                     const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
-                    const float dx = r0.x - pxf, dy = r0.y - pyf;
-                    const float power = splat_power(r0.z, r0.w, r1.x, dx, dy);
-                    if (power > 0.0f) continue;
-                    const float alpha = splat_alpha(r1.y, splat_exp(power));
-                    if (alpha < GS_ALPHA_MIN) continue;
-                    const float test_T = T * (1.0f - alpha);
-                    if (test_T < GS_T_MIN) { done = true; break; }
-                    const float4 r2 = rec[j * 3 + 2];
-                    const float w = alpha * T;
-                    C0 += r2.x * w; C1 += r2.y * w; C2 += r2.z * w;
-                    D += r1.z * w;
-                    A += w;
-                    T = test_T;
-                    last = (uint32_t)(c * CHUNK + j + 1);
+                    const ColTerms ct = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf));
+                    float pw[PX];
+                    unsigned pass = 0;
+                    #pragma unroll
+                    for (int k = 0; k < PX; k++) {
+                        pw[k] = splat_power(ct, __fsub_rn(r0.y, pyf[k]));
+                        if (pw[k] >= r1.w && pw[k] <= 0.0f) pass |= 1u << k;
+                    }
+                    pass &= ~done;
+                    if (pass) {
+                        const float4 r2 = rec[j * 3 + 2];
+                        #pragma unroll
+                        for (int k = 0; k < PX; k++) {
+                            if (pass & (1u << k)) {
+                                const float alpha = splat_alpha(r1.y, splat_exp(pw[k]));
+                                const float test_T = next_T(T[k], alpha);
+                                const bool visible = alpha >= GS_ALPHA_MIN;
+                                const bool blend = visible && !(test_T < GS_T_MIN);
+                                if (visible && !blend) done |= 1u << k;
+                                if (blend) {
+                                    const float w = __fmul_rn(alpha, T[k]);
+                                    C0[k] = __fmaf_rn(r2.x, w, C0[k]);
+                                    C1[k] = __fmaf_rn(r2.y, w, C1[k]);
+                                    C2[k] = __fmaf_rn(r2.z, w, C2[k]);
+                                    D[k] = __fmaf_rn(r1.z, w, D[k]);
+                                    A[k] = __fadd_rn(A[k], w);
+                                    T[k] = test_T;
+                                    last[k] = (uint32_t)(c * CHUNK + j + 1);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             }
-            const int ndone = __syncthreads_count(done);
-            if (ndone == BLEND_THREADS) {
+            const int all_done = __syncthreads_and(done == 0xFu);
+            if (all_done) {
                 if (have_next) { mbar_wait(&s_bar[cur ^ 1], (phases >> (cur ^ 1)) & 1u); phases ^= 1u << (cur ^ 1); }   // drain prefetch
                 break;
             }
         }
-        if (tc.inside) {
+        {
             const float* __restrict__ bg = p.cams + (size_t)tc.v * GS_CAM_FLOATS + GS_CAM_BG;
-            const size_t pix = (size_t)tc.py * p.W + tc.px;
+            const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
             const size_t vb = (size_t)tc.v * HW;
-            p.final_T[vb + pix] = T;
-            p.n_contrib[vb + pix] = last;
-            out_color[vb * 3 + pix] = C0 + T * bg[0];
-            out_color[vb * 3 + HW + pix] = C1 + T * bg[1];
-            out_color[vb * 3 + 2 * HW + pix] = C2 + T * bg[2];
-            out_depth[vb + pix] = D;
-            out_alpha[vb + pix] = A;
+            #pragma unroll
+            for (int k = 0; k < PX; k++) {
+                if (outside & (1u << k)) continue;
+                const size_t pix = (size_t)(tc.ty0 + cy + 4 * k) * p.W + px;
+                p.final_T[vb + pix] = T[k];
+                p.n_contrib[vb + pix] = last[k];
+                out_color[vb * 3 + pix] = __fmaf_rn(T[k], b0, C0[k]);
+                out_color[vb * 3 + HW + pix] = __fmaf_rn(T[k], b1, C1[k]);
+                out_color[vb * 3 + 2 * HW + pix] = __fmaf_rn(T[k], b2, C2[k]);
+                out_depth[vb + pix] = D[k];
+                out_alpha[vb + pix] = A[k];
+            }
         }
     }
 }
@@ -149,119 +263,144 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
 // slot s of the butterfly -> float index inside the 12-float grad2d record
 __device__ __forceinline__ int slot_to_float(int s) { return s < 7 ? s : s + 1; }
 
-__global__ void __launch_bounds__(BLEND_THREADS)
-blend_bwd_kernel(const GsParams p, const float* __restrict__ g_color, const float* __restrict__ g_depth,
-                 const float* __restrict__ g_alpha)
+__global__ void __launch_bounds__(BT)
+blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
 {
     __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
-    __shared__ __align__(16) float s_acc[CHUNK * GS_REC_FLOATS];
+    __shared__ __align__(16) float s_acc[2][CHUNK * GS_REC_FLOATS];     // one private slot array per warp
+    __shared__ unsigned long long s_touched[2];                         // bit j: warp w wrote s_acc[w][j]
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_max[BLEND_THREADS / 32];
+    __shared__ uint32_t s_max[2];
+    __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cx = warp * 8 + (lane & 7), cy = lane >> 3;
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
     __syncthreads();
-    uint32_t phases = 0u;                       // bit b = parity to wait for on s_bar[b]
+    uint32_t phases = 0u;
     const size_t HW = (size_t)p.H * p.W;
-    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
     const bool hi4 = lane & 16, hi3 = lane & 8, hi2 = lane & 4, hi1 = lane & 2;
     const int my_slot = lane >> 1;
+    float* __restrict__ my_acc = s_acc[warp];
 
-    for (long long tg = blockIdx.x; tg < p.total_tiles; tg += gridDim.x) {
-        const TileCtx tc = tile_ctx(p, tg, lx, ly);
-        if (tc.n == 0) continue;                               // uniform per CTA
-        const float pxf = (float)tc.px, pyf = (float)tc.py;
-        const size_t vb = (size_t)tc.v * HW;
-        const size_t pix = (size_t)tc.py * p.W + tc.px;
-        float T_final = 0.f, gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, gd = 0.f, ga = 0.f;
-        uint32_t last = 0;
-        if (tc.inside) {
-            T_final = p.final_T[vb + pix];
-            last = p.n_contrib[vb + pix];
-            gc0 = g_color[vb * 3 + pix]; gc1 = g_color[vb * 3 + HW + pix]; gc2 = g_color[vb * 3 + 2 * HW + pix];
-            if (g_depth) gd = g_depth[vb + pix];
-            if (g_alpha) ga = g_alpha[vb + pix];
+    for (;;) {
+        if (tid == 0) {
+            const unsigned i = atomicAdd(&p.status->q_bwd_heavy, 1u);
+            s_item = i < p.status->num_active ? (long long)p.active_tiles[i] : ITEM_DONE;
         }
-        uint32_t m = last;
+        __syncthreads();
+        const long long item = s_item;
+        __syncthreads();
+        if (item == ITEM_DONE) break;
+
+        const TileCtx tc = tile_ctx(p, item);
+        const int px = tc.tx0 + cx;
+        const float pxf = (float)px;
+        const size_t vb = (size_t)tc.v * HW;
+        const float* __restrict__ bg = p.cams + (size_t)tc.v * GS_CAM_FLOATS + GS_CAM_BG;
+        const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+
+        // per-pixel state: T (recovered back-to-front), suffix sums B of what lies behind, loss gradients
+        float pyf[PX], T[PX], B0[PX], B1[PX], B2[PX], Bd[PX], Ba[PX], g0[PX], g1[PX], g2[PX], gd[PX], ga[PX], tfbg[PX];
+        uint32_t last[PX];
+        #pragma unroll
+        for (int k = 0; k < PX; k++) {
+            const int py = tc.ty0 + cy + 4 * k;
+            pyf[k] = (float)py;
+            B0[k] = B1[k] = B2[k] = Bd[k] = Ba[k] = 0.f;
+            T[k] = 0.f; last[k] = 0u; g0[k] = g1[k] = g2[k] = gd[k] = ga[k] = 0.f;
+            if (px < p.W && py < p.H) {
+                const size_t pix = (size_t)py * p.W + px;
+                T[k] = p.final_T[vb + pix];
+                last[k] = p.n_contrib[vb + pix];
+                g0[k] = io.dL_dcolor[vb * 3 + pix]; g1[k] = io.dL_dcolor[vb * 3 + HW + pix]; g2[k] = io.dL_dcolor[vb * 3 + 2 * HW + pix];
+                if (io.dL_ddepth) gd[k] = io.dL_ddepth[vb + pix];
+                if (io.dL_dalpha) ga[k] = io.dL_dalpha[vb + pix];
+            }
+            tfbg[k] = T[k] * (b0 * g0[k] + b1 * g1[k] + b2 * g2[k]);             // T_final * (bg . dL/dC)
+        }
+        uint32_t m = max(max(last[0], last[1]), max(last[2], last[3]));
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (lane == 0) s_max[warp] = m;
         __syncthreads();
-        uint32_t nmax = 0;
-        #pragma unroll
-        for (int w = 0; w < BLEND_THREADS / 32; w++) nmax = max(nmax, s_max[w]);
-        nmax = min(nmax, (uint32_t)tc.n);
-        __syncthreads();                                       // s_max is rewritten by the next tile
-        if (nmax == 0) continue;                               // uniform
+        const int nmax = (int)min(max(s_max[0], s_max[1]), (uint32_t)tc.n);
+        if (nmax == 0) continue;                                // uniform; the next __syncthreads is after the fetch
 
-        const float* __restrict__ bg = p.cams + (size_t)tc.v * GS_CAM_FLOATS + GS_CAM_BG;
-        const float bg_dot = bg[0] * gc0 + bg[1] * gc1 + bg[2] * gc2;
-        float T = T_final, last_alpha = 0.f;
-        float rc0 = 0.f, rc1 = 0.f, rc2 = 0.f, rd = 0.f, ra = 0.f;      // "colour behind" recursions
-        float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
-
-        const int nchunks = ((int)nmax + CHUNK - 1) / CHUNK;
+        const int nchunks = (nmax + CHUNK - 1) / CHUNK;
         const float4* __restrict__ src = p.sorted_rec + tc.start * 3;
         float4* __restrict__ gbase = p.grad2d + (size_t)tc.v * p.N * 3;
         if (tid == 0) {
             const int c = nchunks - 1;
-            const uint32_t bytes = (uint32_t)min((int)nmax - c * CHUNK, CHUNK) * REC_BYTES;
+            const uint32_t bytes = (uint32_t)(nmax - c * CHUNK) * REC_BYTES;
             mbar_expect_tx(&s_bar[0], bytes);
             bulk_g2s(s_rec[0], src + (size_t)c * CHUNK * 3, bytes, &s_bar[0]);
         }
-        for (int k = 0; k < nchunks; k++) {
-            const int c = nchunks - 1 - k, cur = k & 1;
+        for (int kc = 0; kc < nchunks; kc++) {
+            const int c = nchunks - 1 - kc, cur = kc & 1;
             if (c > 0 && tid == 0) {
-                const uint32_t bytes = (uint32_t)CHUNK * REC_BYTES;          // every earlier chunk is full
+                const uint32_t bytes = (uint32_t)CHUNK * REC_BYTES;              // every earlier chunk is full
                 mbar_expect_tx(&s_bar[cur ^ 1], bytes);
                 bulk_g2s(s_rec[cur ^ 1], src + (size_t)(c - 1) * CHUNK * 3, bytes, &s_bar[cur ^ 1]);
             }
-            for (int t = tid; t < CHUNK * 3; t += BLEND_THREADS)
-                reinterpret_cast<float4*>(s_acc)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();
             mbar_wait(&s_bar[cur], (phases >> cur) & 1u);
             phases ^= 1u << cur;
-            const int cnt = min((int)nmax - c * CHUNK, CHUNK);
+            const int cnt = min(nmax - c * CHUNK, CHUNK);
             const float4* __restrict__ rec = s_rec[cur];
+            unsigned long long touched = 0ull;                  // warp-uniform
             for (int j = cnt - 1; j >= 0; j--) {
                 const uint32_t idx = (uint32_t)(c * CHUNK + j);
                 const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
-                const float dx = r0.x - pxf, dy = r0.y - pyf;
-                const float power = splat_power(r0.z, r0.w, r1.x, dx, dy);
-                const float G = splat_exp(power);
-                const float alpha = splat_alpha(r1.y, G);
-                const bool contrib = (idx < last) && (power <= 0.0f) && (alpha >= GS_ALPHA_MIN);
-                if (!__any_sync(0xffffffffu, contrib)) continue;
+                const float dx = __fsub_rn(r0.x, pxf);
+                const ColTerms ct = col_terms(r0.z, r0.w, r1.x, dx);
+                float pw[PX], dyk[PX];
+                unsigned pass = 0;
+                #pragma unroll
+                for (int k = 0; k < PX; k++) {
+                    dyk[k] = __fsub_rn(r0.y, pyf[k]);
+                    pw[k] = splat_power(ct, dyk[k]);
+                    if (pw[k] >= r1.w && pw[k] <= 0.0f && idx < last[k]) pass |= 1u << k;
+                }
+                if (!__any_sync(0xffffffffu, pass != 0u)) continue;
                 float r[16];
                 #pragma unroll
                 for (int s = 0; s < 16; s++) r[s] = 0.f;
-                if (contrib) {
+                if (pass) {
                     const float4 r2 = rec[j * 3 + 2];
-                    T = T / (1.0f - alpha);
-                    const float w = alpha * T;
-                    float dL_dalpha;
-                    rc0 = last_alpha * lc0 + (1.f - last_alpha) * rc0; lc0 = r2.x;
-                    rc1 = last_alpha * lc1 + (1.f - last_alpha) * rc1; lc1 = r2.y;
-                    rc2 = last_alpha * lc2 + (1.f - last_alpha) * rc2; lc2 = r2.z;
-                    dL_dalpha = (r2.x - rc0) * gc0 + (r2.y - rc1) * gc1 + (r2.z - rc2) * gc2;
-                    rd = last_alpha * ld + (1.f - last_alpha) * rd; ld = r1.z;
-                    dL_dalpha += (r1.z - rd) * gd;
-                    ra = last_alpha + (1.f - last_alpha) * ra;
-                    dL_dalpha += (1.f - ra) * ga;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                    const float dL_dG = r1.y * dL_dalpha;          // straight-through the 0.99 cap
-                    const float gdx = G * dx, gdy = G * dy;
-                    r[0] = dL_dG * (-gdx * r0.z - gdy * r0.w);     // d/dpix.x
-                    r[1] = dL_dG * (-gdy * r1.x - gdx * r0.w);     // d/dpix.y
-                    r[2] = -0.5f * gdx * dx * dL_dG;               // d/dconA
-                    r[3] = -gdx * dy * dL_dG;                      // d/dconB (true, not halved)
-                    r[4] = -0.5f * gdy * dy * dL_dG;               // d/dconC
-                    r[5] = G * dL_dalpha;                          // d/dopacity
-                    r[6] = w * gd;                                 // d/ddepth
-                    r[7] = w * gc0; r[8] = w * gc1; r[9] = w * gc2;
+                    #pragma unroll
+                    for (int k = 0; k < PX; k++) {
+                        if (pass & (1u << k)) {
+                            const float G = splat_exp(pw[k]);
+                            const float alpha = splat_alpha(r1.y, G);
+                            if (alpha >= GS_ALPHA_MIN) {
+                                const float ra = __fdividef(1.0f, __fsub_rn(1.0f, alpha));
+                                const float Tk = T[k] * ra;                      // undoes the forward's T*(1-alpha)
+                                const float w = __fmul_rn(alpha, Tk);
+                                // dL/dalpha_i = sum_ch (c_i T_i - B/(1-alpha_i)) g_ch  (+ depth, alpha, background terms)
+                                float dLda = (r2.x * Tk - B0[k] * ra) * g0[k] + (r2.y * Tk - B1[k] * ra) * g1[k] + (r2.z * Tk - B2[k] * ra) * g2[k];
+                                dLda += (r1.z * Tk - Bd[k] * ra) * gd[k];
+                                dLda += (Tk - Ba[k] * ra) * ga[k];
+                                dLda -= tfbg[k] * ra;
+                                B0[k] = __fmaf_rn(r2.x, w, B0[k]);
+                                B1[k] = __fmaf_rn(r2.y, w, B1[k]);
+                                B2[k] = __fmaf_rn(r2.z, w, B2[k]);
+                                Bd[k] = __fmaf_rn(r1.z, w, Bd[k]);
+                                Ba[k] = __fadd_rn(Ba[k], w);
+                                const float dL_dG = r1.y * dLda;                 // straight-through the 0.99 cap
+                                const float gdx = G * dx, gdy = G * dyk[k];
+                                r[0] += dL_dG * (-gdx * r0.z - gdy * r0.w);      // d/dpix.x
+                                r[1] += dL_dG * (-gdy * r1.x - gdx * r0.w);      // d/dpix.y
+                                r[2] += -0.5f * gdx * dx * dL_dG;                // d/dconA
+                                r[3] += -gdx * dyk[k] * dL_dG;                   // d/dconB (true, not halved)
+                                r[4] += -0.5f * gdy * dyk[k] * dL_dG;            // d/dconC
+                                r[5] += G * dLda;                                // d/dopacity
+                                r[6] += w * gd[k];                               // d/ddepth
+                                r[7] += w * g0[k]; r[8] += w * g1[k]; r[9] += w * g2[k];
+                                T[k] = Tk;
+                            }
+                        }
+                    }
                 }
-                // halving butterfly: after it, lane pair (2s, 2s+1) holds the warp total of slot s
+                // halving butterfly: afterwards lane pair (2s, 2s+1) holds the warp total of slot s
                 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const float send = hi4 ? r[i] : r[8 + i];
@@ -286,40 +425,47 @@ blend_bwd_kernel(const GsParams p, const float* __restrict__ g_color, const floa
                     r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
                 }
                 r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-                if (!(lane & 1) && my_slot < 10) atomicAdd(&s_acc[j * GS_REC_FLOATS + slot_to_float(my_slot)], r[0]);
+                if (!(lane & 1) && my_slot < 10) my_acc[j * GS_REC_FLOATS + slot_to_float(my_slot)] = r[0];
+                touched |= 1ull << j;
             }
+            if (lane == 0) s_touched[warp] = touched;
             __syncthreads();
-            for (int t = tid; t < cnt * 3; t += BLEND_THREADS) {
-                const float4 a = reinterpret_cast<const float4*>(s_acc)[t];
-                if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) {
-                    const int j = t / 3, part = t - j * 3;
-                    const int id = __float_as_int(rec[j * 3 + 1].w);
-                    red_add_v4(gbase + (size_t)id * 3 + part, a);
-                }
+            const unsigned long long t0 = s_touched[0], t1 = s_touched[1];
+            for (int t = tid; t < cnt * 3; t += BT) {
+                const int j = t / 3, part = t - j * 3;
+                const bool a0 = (t0 >> j) & 1ull, a1 = (t1 >> j) & 1ull;
+                if (!(a0 || a1)) continue;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a0) a = reinterpret_cast<const float4*>(s_acc[0])[t];
+                if (a1) { const float4 b = reinterpret_cast<const float4*>(s_acc[1])[t]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+                if (part != 0) a.w = 0.f;                      // floats 7 and 11 of the record are never written
+                const int id = __float_as_int(rec[j * 3 + 2].w);
+                red_add_v4(gbase + (size_t)id * 3 + part, a);
             }
             __syncthreads();
         }
     }
 }
 
-}  // namespace
-
-static unsigned persistent_grid(long long total_tiles, int num_sms, int ctas_per_sm)
+int resident_ctas(const void* kernel, int block, int num_sms, int fallback_per_sm)
 {
-    long long blocks = total_tiles;
-    const long long maxb = (long long)num_sms * ctas_per_sm;
-    if (blocks > maxb) blocks = maxb;
-    if (blocks < 1) blocks = 1;
-    return (unsigned)blocks;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = fallback_per_sm;
+    return per_sm * num_sms;
 }
+
+}  // namespace
 
 void gs_launch_blend_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s)
 {
-    blend_fwd_kernel<<<persistent_grid(p.total_tiles, num_sms, 8), BLEND_THREADS, 0, s>>>(p, color, depth, alpha);
+    static thread_local int grid = 0, grid_sms = 0;
+    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_fwd_kernel, BT, num_sms, 16); grid_sms = num_sms; }
+    blend_fwd_kernel<<<grid, BT, 0, s>>>(p, color, depth, alpha);
 }
 
-void gs_launch_blend_bwd(const GsParams& p, const float* g_color, const float* g_depth, const float* g_alpha,
-                         int num_sms, cudaStream_t s)
+void gs_launch_blend_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms, cudaStream_t s)
 {
-    blend_bwd_kernel<<<persistent_grid(p.total_tiles, num_sms, 6), BLEND_THREADS, 0, s>>>(p, g_color, g_depth, g_alpha);
+    static thread_local int grid = 0, grid_sms = 0;
+    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_bwd_kernel, BT, num_sms, 8); grid_sms = num_sms; }
+    blend_bwd_kernel<<<grid, BT, 0, s>>>(p, io);
 }

@@ -5,9 +5,11 @@
 //   tile_count    u32 [V*T + 1]                     instances per (view, tile)
 //   tile_start    u32 [V*T + 1]                     exclusive scan of tile_count; [V*T] = I
 //   tile_fill     u32 [V*T]                         scatter cursors
+//   active_tiles  u32 [V*T]                         compacted list of non-empty (view,tile) ids (order arbitrary)
 //   block_sums    u32 [scan blocks]                 scan scratch
 //   clamped       u8  [V*N]                         SH clamp bits (r,g,b)
-//   geom          48-byte record [V*N]              (x,y,conA,conB | conC,opacity,depth,id | r,g,b,_)
+//   geom          48-byte record [V*N]              (x,y,conA,conB | conC,opacity,depth,thr | r,g,b,id)
+//                                                   thr = conservative lower bound of `power` for alpha >= 1/255
 //   pairs         u64 [cap]                         (depth_bits<<32 | id), tile-major, unsorted
 //   sorted_ids    u32 [cap]
 //   sorted_rec    48-byte record [cap]              tile-sorted copy of geom: ONE contiguous bulk copy per chunk
@@ -33,11 +35,17 @@ struct GsStatusDev {
     unsigned long long cap_instances;
     int overflow;
     int max_tile_instances;
+    // work queues of the persistent blend kernels (device-side dynamic scheduling)
+    unsigned int num_active;            // non-empty (view, tile) pairs listed in active_tiles[]
+    unsigned int q_fwd_heavy;           // next index into active_tiles[] (forward)
+    unsigned int q_fwd_fill;            // next group of GS_FILL_GROUP tiles to background-fill (forward)
+    unsigned int q_bwd_heavy;           // next index into active_tiles[] (backward)
     int pad[2];
 };
+#define GS_FILL_GROUP 16
 
 struct GsLayout {
-    size_t off_status, off_tile_count, off_tile_start, off_tile_fill, off_block_sums, off_clamped, off_geom,
+    size_t off_status, off_tile_count, off_tile_start, off_tile_fill, off_active, off_block_sums, off_clamped, off_geom,
            off_pairs, off_sorted_ids, off_sorted_rec, off_final_T, off_n_contrib, off_grad2d, total;
     int tiles_x, tiles_y, tiles;        // per view
     long long total_tiles;              // V * tiles
@@ -65,6 +73,7 @@ static inline GsLayout gs_make_layout(int N, int V, int H, int W, long long cap)
     L.off_tile_count = o;  o = gs_align_up(o + 4 * (size_t)(L.total_tiles + 1), A);
     L.off_tile_start = o;  o = gs_align_up(o + 4 * (size_t)(L.total_tiles + 1), A);
     L.off_tile_fill = o;   o = gs_align_up(o + 4 * (size_t)(L.total_tiles + 1), A);
+    L.off_active = o;      o = gs_align_up(o + 4 * (size_t)(L.total_tiles + 1), A);
     L.off_block_sums = o;  o = gs_align_up(o + 4 * (size_t)(L.scan_blocks + 1), A);
     L.off_clamped = o;     o = gs_align_up(o + VN, A);
     L.off_geom = o;        o = gs_align_up(o + 48 * VN, A);
@@ -87,7 +96,7 @@ struct GsParams {
     float mod;
     const float *means3D, *shs, *colors, *opac, *scales, *rots, *cov3D, *cams;
     GsStatusDev* status;
-    uint32_t *tile_count, *tile_start, *tile_fill, *block_sums;
+    uint32_t *tile_count, *tile_start, *tile_fill, *active_tiles, *block_sums;
     uint8_t* clamped;
     float4* geom;
     unsigned long long* pairs;
@@ -106,8 +115,7 @@ void gs_launch_mark_visible(int N, const float* means3D, const float* cam, uint8
 void gs_launch_tile_scan(const GsParams& p, cudaStream_t s);
 void gs_launch_sort_gather(const GsParams& p, int num_sms, cudaStream_t s);
 void gs_launch_blend_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s);
-void gs_launch_blend_bwd(const GsParams& p, const float* g_color, const float* g_depth, const float* g_alpha,
-                         int num_sms, cudaStream_t s);
+void gs_launch_blend_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms, cudaStream_t s);
 void gs_launch_preprocess_bwd(const GsParams& p, const GsBackwardIO& io, cudaStream_t s);
 
 #ifdef __CUDACC__

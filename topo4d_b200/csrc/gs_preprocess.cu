@@ -164,8 +164,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const GsParams p, int32
     p.clamped[gid] = (uint8_t)clampbits;
     float4* g = p.geom + gid * 3;
     g[0] = make_float4(pix_x, pix_y, cA, cB);
-    g[1] = make_float4(cC, p.opac[i], tz, __int_as_float(i));
-    g[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+    // thr: the blend kernels skip a pixel without evaluating exp() when power < thr.  alpha >= 1/255 needs
+    // power >= -ln(255*opacity); the 1e-3 margin (0.1 % in alpha) dwarfs any fp32 rounding of power or exp,
+    // so the prefilter can only pass extra pixels (which then fail the exact alpha test), never drop one.
+    const float opac = p.opac[i];
+    const float thr = opac > 0.0f ? -logf(255.0f * opac) - 1.0e-3f : __int_as_float(0x7f800000);
+    g[1] = make_float4(cC, opac, tz, thr);
+    g[2] = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(i));
 
     // count this splat in every tile of its rectangle
     uint32_t* cnt = p.tile_count + (size_t)v * p.tiles;
