@@ -133,6 +133,7 @@ extern "C" int gs_forward_stages(const GsProblem* p, const GsForwardOut* out, ui
     }
     const int sms = sm_count();
     if (stages & GS_FWD_SORT) {
+        CK(cudaMemsetAsync(&q.status->q_sort, 0, sizeof(unsigned int), s));
         gs_launch_sort_gather(q, sms, s);
         CK_LAUNCH("sort_gather_kernel");
     }

@@ -169,8 +169,18 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nt
 __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParams p)
 {
     __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
+    __shared__ long long s_tile;
     const int tid = threadIdx.x;
-    for (long long tg = blockIdx.x; tg < p.total_tiles; tg += gridDim.x) {
+    // non-empty tiles come from the device-side queue the scan kernel filled (dynamic load balance)
+    for (;;) {
+        if (tid == 0) {
+            const unsigned i = atomicAdd(&p.status->q_sort, 1u);
+            s_tile = i < p.status->num_active ? (long long)p.active_tiles[i] : -1;
+        }
+        __syncthreads();
+        const long long tg = s_tile;
+        __syncthreads();
+        if (tg < 0) break;
         unsigned long long start = p.tile_start[tg], end = p.tile_start[tg + 1];
         if (end > (unsigned long long)p.cap) end = (unsigned long long)p.cap;
         if (start >= end) continue;

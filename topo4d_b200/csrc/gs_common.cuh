@@ -40,7 +40,8 @@ struct GsStatusDev {
     unsigned int q_fwd_heavy;           // next index into active_tiles[] (forward)
     unsigned int q_fwd_fill;            // next group of GS_FILL_GROUP tiles to background-fill (forward)
     unsigned int q_bwd_heavy;           // next index into active_tiles[] (backward)
-    int pad[2];
+    unsigned int q_sort;                // next index into active_tiles[] (sort + gather)
+    int pad[1];
 };
 #define GS_FILL_GROUP 16
 
