@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--ref-views-per-step", type=int, default=4, help="views per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--blend-px", type=int, default=0, help="force the blend kernels' pixels per thread (0 = auto)")
     return ap.parse_args()
 
 
@@ -193,7 +194,7 @@ def run_ours(a):
         return engine.forward(params["means3D"], params["opacities"], cam_groups[g], H, W, shs=params.get("shs"),
                               colors_precomp=params.get("colors_precomp"), scales=params["scales"],
                               rotations=params["rotations"], sh_degree=a.sh_degree if use_sh else 0, check="none",
-                              cap_instances=caps[g], stage_events=ev)
+                              cap_instances=caps[g], stage_events=ev, blend_px=a.blend_px or None)
 
     # size capacities once (synchronising) and build the fixed dL/dpixel images of
     # L = L1(color, target) + 0.1 mean(depth) + 0.1 mean(alpha)  (SSIM excluded)

@@ -61,6 +61,10 @@ typedef struct GsProblem {
     int32_t sh_coeffs;              /* M: coefficients stored per Gaussian in `shs` [N,M,3]   */
     float   scale_modifier;
     int32_t debug;                  /* !=0: synchronise + check after every stage             */
+    int32_t blend_px;               /* tuning hint: pixels per thread in the blend kernels: 4 (many non-empty
+                                       tiles: fewest instructions), 2 or 1 (few tiles: more warps per tile,
+                                       lower latency); 0 = library default (4).  Never changes results.   */
+    int32_t reserved0;              /* must be 0 */
     int64_t cap_instances;          /* capacity (tile,Gaussian) instances of the workspace    */
     /* inputs, DEVICE pointers, fp32, contiguous.  Exactly one of shs|colors_precomp and
        exactly one of (scales,rotations)|cov3D_precomp must be non-NULL. */
@@ -105,6 +109,8 @@ typedef struct GsStatus {           /* host copy of the device status block */
     int64_t cap_instances;
     int32_t overflow;               /* 1 if num_instances > cap_instances (outputs invalid)  */
     int32_t max_tile_instances;     /* longest per-tile list                                 */
+    int32_t num_active_tiles;       /* non-empty (view, tile) pairs: what blend_px should be chosen from */
+    int32_t reserved0;
 } GsStatus;
 
 /* Byte size of the workspace for (N, V, H, W, cap_instances).  Pure host arithmetic. */

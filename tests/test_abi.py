@@ -30,10 +30,10 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_struct_layouts_match_header_sizes():
     # natural alignment on LP64: GsProblem = 8 ints/floats (32) + i64 + 8 pointers + pointer + size_t
-    assert C.sizeof(_lib.GsProblem) == 32 + 8 + 8 * 8 + 8 + 8
+    assert C.sizeof(_lib.GsProblem) == 40 + 8 + 8 * 8 + 8 + 8
     assert C.sizeof(_lib.GsForwardOut) == 4 * 8
     assert C.sizeof(_lib.GsBackwardIO) == 12 * 8
-    assert C.sizeof(_lib.GsStatus) == 24
+    assert C.sizeof(_lib.GsStatus) == 32
     assert C.sizeof(_lib.GsWorkspaceView) == 7 * 8 + 8
 
 

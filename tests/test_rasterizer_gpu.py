@@ -134,3 +134,26 @@ def test_forward_is_deterministic_and_backward_close():
     ga = engine.backward(a[4], gc).flat
     gb = engine.backward(b[4], gc).flat
     assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-5 * float(ga.abs().max()))   # atomics reorder fp32 sums
+
+
+def test_blend_px_variants_agree():
+    """The pixels-per-thread tuning hint (4 / 2 / 1) never changes results: forward bit-identical, backward equal
+    up to the order of fp32 partial sums."""
+    dev = torch.device("cuda:0")
+    sc = synth.random_scene(4000, seed=21, sh_degree=1)
+    t = {k: torch.tensor(v, device=dev) for k, v in sc.items()}
+    cams = [synth.front_camera(200, 137), synth.make_camera(synth.look_at((2.0, 1.0, -3.0)), 200, 137, 150.0, 150.0)]
+    cam = torch.tensor(engine.pack_cameras_numpy(cams, (0.2, 0.1, 0.3)), device=dev)
+    kw = dict(shs=t["shs"], scales=t["scales"] * 2.0, rotations=t["rotations"], sh_degree=1)
+    ref = engine.forward(t["means3D"], t["opacities"], cam, 137, 200, blend_px=4, **kw)
+    gc, gd, ga = torch.randn_like(ref[0]), torch.randn_like(ref[2]), torch.randn_like(ref[3])
+    gref = engine.backward(ref[4], gc, gd, ga).flat
+    for px in (2, 1):
+        out = engine.forward(t["means3D"], t["opacities"], cam, 137, 200, blend_px=px, **kw)
+        for k in range(4):
+            assert torch.equal(out[k], ref[k]), (px, k)
+        v0, v1 = ref[4].view(), out[4].view()
+        assert torch.equal(v0["n_contrib"], v1["n_contrib"]) and torch.equal(v0["final_T"], v1["final_T"])
+        g = engine.backward(out[4], gc, gd, ga).flat
+        assert torch.allclose(g, gref, rtol=2e-4, atol=2e-5 * float(gref.abs().max())), px
+    assert engine.pick_blend_px(None) == 4 and engine.pick_blend_px(10000) == 4 and engine.pick_blend_px(2000) == 2 and engine.pick_blend_px(300) == 1

@@ -21,7 +21,7 @@ _vp = C.c_void_p
 class GsProblem(C.Structure):
     _fields_ = [("N", C.c_int32), ("V", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32), ("scale_modifier", C.c_float),
-                ("debug", C.c_int32), ("cap_instances", C.c_int64),
+                ("debug", C.c_int32), ("blend_px", C.c_int32), ("reserved0", C.c_int32), ("cap_instances", C.c_int64),
                 ("means3D", _vp), ("shs", _vp), ("colors_precomp", _vp), ("opacities", _vp), ("scales", _vp),
                 ("rotations", _vp), ("cov3D_precomp", _vp), ("cameras", _vp),
                 ("workspace", _vp), ("workspace_bytes", C.c_size_t)]
@@ -39,7 +39,7 @@ class GsBackwardIO(C.Structure):
 
 class GsStatus(C.Structure):
     _fields_ = [("num_instances", C.c_int64), ("cap_instances", C.c_int64), ("overflow", C.c_int32),
-                ("max_tile_instances", C.c_int32)]
+                ("max_tile_instances", C.c_int32), ("num_active_tiles", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class GsWorkspaceView(C.Structure):

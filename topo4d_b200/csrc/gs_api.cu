@@ -78,6 +78,7 @@ static GsParams make_params(const GsProblem* p, const GsLayout& L)
     q.n_contrib = (uint32_t*)(ws + L.off_n_contrib);
     q.grad2d = (float4*)(ws + L.off_grad2d);
     q.scan_blocks = L.scan_blocks;
+    q.blend_px = p->blend_px;
     return q;
 }
 
@@ -186,6 +187,8 @@ extern "C" int gs_read_status(const GsProblem* p, GsStatus* st, gs_stream_t stre
     st->cap_instances = (int64_t)d.cap_instances;
     st->overflow = d.overflow;
     st->max_tile_instances = d.max_tile_instances;
+    st->num_active_tiles = (int32_t)(d.num_long + d.num_short);
+    st->reserved0 = 0;
     return d.overflow ? GS_E_OVERFLOW : 0;
 }
 

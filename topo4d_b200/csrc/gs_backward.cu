@@ -2,11 +2,12 @@
 // scales, rotations, SH | colours, opacities} (+ means2D in NDC-scaled units, + cov3D_precomp).
 //
 // Replaces upstream computeCov2DCUDA + preprocessCUDA (backward) behind GaussianRasterizer's
-// autograd backward (reference: loss.backward() at train.py:667,738).  One thread owns one Gaussian
-// and walks the V views of the batch, re-deriving the cheap forward intermediates (cov3D, J, T)
-// instead of storing them, and accumulates in registers, so every output element is written exactly
-// once, coalesced, with no atomics -- the caller may point the outputs into one flat buffer that a
-// single NCCL all-reduce then sums across view-parallel ranks.
+// autograd backward (reference: loss.backward() at train.py:667,738).  Four adjacent lanes own one
+// Gaussian and split the V views of the batch (lane q takes views q, q+4, ...), re-deriving the cheap
+// forward intermediates (cov3D, J, T) instead of storing them and accumulating in registers; two
+// shuffle steps combine the four partial sums and one lane writes, so every output element is written
+// exactly once with no atomics -- the caller may point the outputs into one flat buffer that a single
+// NCCL all-reduce then sums across view-parallel ranks.
 // Conventions: frustum-clamped t.x/t.y are constants, SH max(0,.) kills the
 // gradient where clamped, depth = view-space z, mean2D gradient reported x(0.5W, 0.5H).
 #include "gs_common.cuh"
@@ -54,11 +55,13 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float* b, fl
 }
 
 template <int K>   // K = (deg+1)^2 active SH coefficients, 0 = colors_precomp
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.N) return;
+    const int t_global = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i_raw = t_global >> 2, vq = t_global & 3;     // Gaussian, view sub-lane
+    const bool act = i_raw < p.N;                            // inactive lanes still take part in the shuffles
+    const int i = act ? i_raw : 0;
     const float px = p.means3D[3 * i], py = p.means3D[3 * i + 1], pz = p.means3D[3 * i + 2];
     const bool use_cov = p.cov3D != nullptr;
 
@@ -96,7 +99,7 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
     #pragma unroll
     for (int k = 0; k < KK * 3; k++) gsh[k] = 0.f;
 
-    for (int v = 0; v < p.V; v++) {
+    for (int v = vq; v < p.V && act; v += 4) {
         const size_t gid = (size_t)v * p.N + i;
         if (io.radii[gid] <= 0) continue;
         const float* __restrict__ cam = p.cams + (size_t)v * GS_CAM_FLOATS;
@@ -116,13 +119,29 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
             const float gr[3] = {(cl & 1u) ? 0.f : a2.x, (cl & 2u) ? 0.f : a2.y, (cl & 4u) ? 0.f : a2.z};
             const float* __restrict__ sh = p.shs + (size_t)i * p.M * 3;
             float gdx = 0.f, gdy = 0.f, gdz = 0.f;
-            #pragma unroll
-            for (int k = 0; k < KK; k++) {
+            if (((p.M * 3) & 3) == 0 && (KK * 3) % 4 == 0) {
+                const float4* __restrict__ sh4 = reinterpret_cast<const float4*>(sh);
                 #pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    gsh[k * 3 + ch] += b[k] * gr[ch];
-                    const float sg = sh[k * 3 + ch] * gr[ch];
-                    gdx += bx[k] * sg; gdy += by[k] * sg; gdz += bz[k] * sg;
+                for (int q4 = 0; q4 < (KK * 3) / 4; q4++) {
+                    const float4 tq = __ldg(sh4 + q4);
+                    const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+                    #pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int idx = 4 * q4 + e, k = idx / 3, ch = idx % 3;
+                        gsh[idx] += b[k] * gr[ch];
+                        const float sg = tv[e] * gr[ch];
+                        gdx += bx[k] * sg; gdy += by[k] * sg; gdz += bz[k] * sg;
+                    }
+                }
+            } else {
+                #pragma unroll
+                for (int k = 0; k < KK; k++) {
+                    #pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        gsh[k * 3 + ch] += b[k] * gr[ch];
+                        const float sg = __ldg(sh + k * 3 + ch) * gr[ch];
+                        gdx += bx[k] * sg; gdy += by[k] * sg; gdz += bz[k] * sg;
+                    }
                 }
             }
             const float dot = gdx * x + gdy * y + gdz * z;
@@ -201,6 +220,23 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
         }
     }
 
+    // combine the four view sub-lanes (lanes 4j..4j+3 of a warp), then lane 0 of the quad writes
+    #pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        #pragma unroll
+        for (int k = 0; k < 3; k++) { gm[k] += __shfl_xor_sync(0xffffffffu, gm[k], o); gcol[k] += __shfl_xor_sync(0xffffffffu, gcol[k], o); }
+        gm2[0] += __shfl_xor_sync(0xffffffffu, gm2[0], o); gm2[1] += __shfl_xor_sync(0xffffffffu, gm2[1], o);
+        gop += __shfl_xor_sync(0xffffffffu, gop, o);
+        #pragma unroll
+        for (int a = 0; a < 3; a++)
+            #pragma unroll
+            for (int c = 0; c < 3; c++) G3[a][c] += __shfl_xor_sync(0xffffffffu, G3[a][c], o);
+        if constexpr (K > 0) {
+            #pragma unroll
+            for (int k = 0; k < KK * 3; k++) gsh[k] += __shfl_xor_sync(0xffffffffu, gsh[k], o);
+        }
+    }
+    if (!act || vq != 0) return;
     io.dL_dmeans3D[3 * i] = gm[0]; io.dL_dmeans3D[3 * i + 1] = gm[1]; io.dL_dmeans3D[3 * i + 2] = gm[2];
     io.dL_dmeans2D[3 * i] = gm2[0]; io.dL_dmeans2D[3 * i + 1] = gm2[1]; io.dL_dmeans2D[3 * i + 2] = 0.f;
     io.dL_dopacities[i] = gop;
@@ -245,7 +281,7 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
 void gs_launch_preprocess_bwd(const GsParams& p, const GsBackwardIO& io, cudaStream_t s)
 {
     if (p.N == 0) return;
-    const int threads = 128, blocks = (p.N + threads - 1) / threads;
+    const int threads = 128, blocks = (int)(((long long)p.N * 4 + threads - 1) / threads);
     if (!p.shs) { preprocess_bwd_kernel<0><<<blocks, threads, 0, s>>>(p, io); return; }
     switch (p.deg) {
         case 0: preprocess_bwd_kernel<1><<<blocks, threads, 0, s>>>(p, io); break;

@@ -95,32 +95,40 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const GsParams
     if (w == 0) { uint32_t x = s_warp[lane]; x = warp_incl_scan(x, lane); s_warp[lane] = x; }
     __syncthreads();
     unsigned long long run = pre + (w > 0 ? s_warp[w - 1] : 0u) + (incl - tsum);
-    uint32_t nact = 0;
+    uint32_t nact = 0;                                   // packed: long count << 16 | short count (<= 4096 per block)
     #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         const long long e = base + k;
         if (e <= n) p.tile_start[e] = (uint32_t)(run > 0xffffffffull ? 0xffffffffull : run);
         if (e < n) p.tile_fill[e] = 0u;
-        if (e < n && c[k] > 0u) nact++;
+        if (e < n && c[k] > 0u) nact += c[k] >= GS_LONG_TILE ? (1u << 16) : 1u;
         run += c[k];
     }
-    // compact the non-empty tiles into active_tiles[] (one atomic per block; order across blocks is arbitrary,
-    // which only changes the order tiles are worked on, never a result)
+    // compact the non-empty tiles into active_tiles[]: long lists from the front, short ones from the back (one
+    // atomic pair per block; the order inside each class is arbitrary, which only changes the order tiles are
+    // worked on, never a result)
     __shared__ uint32_t s_awarp[32];
-    __shared__ uint32_t s_abase;
+    __shared__ uint32_t s_abase[2];
     const uint32_t aincl = warp_incl_scan(nact, lane);
     __syncthreads();
     if (lane == 31) s_awarp[w] = aincl;
     __syncthreads();
     if (w == 0) { uint32_t x = s_awarp[lane]; x = warp_incl_scan(x, lane); s_awarp[lane] = x; }
     __syncthreads();
-    if (threadIdx.x == SCAN_THREADS - 1) s_abase = atomicAdd(&p.status->num_active, s_awarp[31]);
+    if (threadIdx.x == SCAN_THREADS - 1) {
+        s_abase[0] = atomicAdd(&p.status->num_long, s_awarp[31] >> 16);
+        s_abase[1] = atomicAdd(&p.status->num_short, s_awarp[31] & 0xffffu);
+    }
     __syncthreads();
-    uint32_t apos = s_abase + (w > 0 ? s_awarp[w - 1] : 0u) + (aincl - nact);
+    const uint32_t excl = (w > 0 ? s_awarp[w - 1] : 0u) + (aincl - nact);
+    uint32_t pos_long = s_abase[0] + (excl >> 16), pos_short = s_abase[1] + (excl & 0xffffu);
     #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         const long long e = base + k;
-        if (e < n && c[k] > 0u) p.active_tiles[apos++] = (uint32_t)e;
+        if (e < n && c[k] > 0u) {
+            if (c[k] >= GS_LONG_TILE) p.active_tiles[pos_long++] = (uint32_t)e;
+            else p.active_tiles[n - 1 - (long long)(pos_short++)] = (uint32_t)e;
+        }
     }
     if (base <= n && n < base + SCAN_ITEMS) {   // the thread that owns element n holds the grand total
         unsigned long long total = pre + (w > 0 ? s_warp[w - 1] : 0u) + (incl - tsum);
@@ -174,8 +182,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParam
     // non-empty tiles come from the device-side queue the scan kernel filled (dynamic load balance)
     for (;;) {
         if (tid == 0) {
-            const unsigned i = atomicAdd(&p.status->q_sort, 1u);
-            s_tile = i < p.status->num_active ? (long long)p.active_tiles[i] : -1;
+            s_tile = gs_active_tile(p, atomicAdd(&p.status->q_sort, 1u));
         }
         __syncthreads();
         const long long tg = s_tile;

@@ -29,11 +29,15 @@
 
 namespace {
 
-constexpr int BT = 64;                        // threads per CTA = 2 warps, each an 8-column half of the tile
-constexpr int PX = 4;                         // pixels per thread
+// PX = pixels per thread (4, 2 or 1).  A tile is always 256 pixels, so a CTA has 256/PX threads = 8/PX warps;
+// warp w sits at columns 8*(w&1).. and rows (w>>1)*4*PX.., lane (lx,ly) owns pixels (8*(w&1)+lx, base+ly+4k).
+// PX = 4 minimises instructions per (pixel, Gaussian) pair and is used when there are enough non-empty tiles
+// to fill the GPU; PX = 2 / 1 trade instructions for 2x / 4x more warps per tile when there are few tiles
+// (small scenes, one view per GPU): the per-tile latency, not the throughput, bounds those launches.
 constexpr int CHUNK = 64;                     // records per bulk copy (3 KB)
 constexpr uint32_t REC_BYTES = 48;
-constexpr float LOG2E = 1.4426950408889634f;
+[[maybe_unused]] constexpr float LOG2E = 1.4426950408889634f;
+
 
 // ---- per-pair arithmetic shared by forward and backward (identical bits in both) ----
 struct ColTerms { float hC, u, v; };          // power(dy) = dy*(hC*dy + u) + v for a fixed pixel column
@@ -68,7 +72,6 @@ constexpr long long ITEM_DONE = -1;
 __device__ __forceinline__ long long fetch_fwd(const GsParams& p, bool prefer_fill, unsigned n_groups)
 {
     GsStatusDev* st = p.status;
-    const unsigned n_active = st->num_active;
     #pragma unroll
     for (int attempt = 0; attempt < 2; attempt++) {
         const bool fill = (attempt == 0) == prefer_fill;
@@ -76,8 +79,8 @@ __device__ __forceinline__ long long fetch_fwd(const GsParams& p, bool prefer_fi
             const unsigned g = atomicAdd(&st->q_fwd_fill, 1u);
             if (g < n_groups) return -((long long)g + 2);
         } else {
-            const unsigned i = atomicAdd(&st->q_fwd_heavy, 1u);
-            if (i < n_active) return (long long)p.active_tiles[i];
+            const long long t = gs_active_tile(p, atomicAdd(&st->q_fwd_heavy, 1u));
+            if (t >= 0) return t;
         }
     }
     return ITEM_DONE;
@@ -110,15 +113,18 @@ __device__ __forceinline__ void store4(float* __restrict__ plane, size_t pix0, f
     for (int k = 0; k < 4; k++) if (k < valid) plane[pix0 + k] = v;
 }
 
-__global__ void __launch_bounds__(BT)
+template <int PX>
+__global__ void __launch_bounds__(256 / PX)
 blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restrict__ out_depth,
                  float* __restrict__ out_alpha)
 {
+    constexpr int BT = 256 / PX;
     __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cx = warp * 8 + (lane & 7), cy = lane >> 3;          // comb: column cx, rows cy + 4k
+    const int cx = (warp & 1) * 8 + (lane & 7), cy = (warp >> 1) * (4 * PX) + (lane >> 3);   // comb: column cx, rows cy + 4k
+    constexpr unsigned ALL = (1u << PX) - 1u;
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t phases = 0u;                       // bit b = parity to wait for on s_bar[b]
@@ -135,14 +141,14 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
         if (item == ITEM_DONE) break;
 
         if (item < 0) {
-            // ---- background fill of the empty tiles of one group (thread = 4x1 strip, row tid>>2) ----
+            // ---- background fill of the empty tiles of one group (work item = 4x1 pixel strip of one tile) ----
             const long long t0 = (-item - 2) * GS_FILL_GROUP;
-            for (int g = 0; g < GS_FILL_GROUP; g++) {
-                const long long tg = t0 + g;
+            for (int it = tid; it < GS_FILL_GROUP * 64; it += BT) {
+                const long long tg = t0 + (it >> 6);
                 if (tg >= p.total_tiles) break;
                 if (p.tile_start[tg + 1] != p.tile_start[tg]) continue;          // non-empty: a heavy item owns it
                 const TileCtx tc = tile_ctx(p, tg);
-                const int x0 = tc.tx0 + 4 * (tid & 3), y = tc.ty0 + (tid >> 2);
+                const int x0 = tc.tx0 + 4 * (it & 3), y = tc.ty0 + ((it & 63) >> 2);
                 const int valid = y < p.H ? min(4, p.W - x0) : 0;
                 if (valid <= 0) continue;
                 const float* __restrict__ bg = p.cams + (size_t)tc.v * GS_CAM_FLOATS + GS_CAM_BG;
@@ -195,7 +201,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
             // Structured per-record body (no break/continue out of divergent code) closed by __syncwarp(): the
             // warp re-converges every record.  Leaving the loop from inside the divergent blend block makes the
             // compiler re-converge only at loop exit, which serialises the 32 lanes (measured: 12x slower).
-            if (!__all_sync(0xffffffffu, done == 0xFu)) {
+            if (!__all_sync(0xffffffffu, done == ALL)) {
                 #pragma unroll 2
                 for (int j = 0; j < cnt; j++) {
                     const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
@@ -234,7 +240,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
                     __syncwarp();
                 }
             }
-            const int all_done = __syncthreads_and(done == 0xFu);
+            const int all_done = __syncthreads_and(done == ALL);
             if (all_done) {
                 if (have_next) { mbar_wait(&s_bar[cur ^ 1], (phases >> (cur ^ 1)) & 1u); phases ^= 1u << (cur ^ 1); }   // drain prefetch
                 break;
@@ -263,17 +269,19 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
 // slot s of the butterfly -> float index inside the 12-float grad2d record
 __device__ __forceinline__ int slot_to_float(int s) { return s < 7 ? s : s + 1; }
 
-__global__ void __launch_bounds__(BT)
+template <int PX>
+__global__ void __launch_bounds__(256 / PX)
 blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
 {
+    constexpr int BT = 256 / PX, NW = 8 / PX;
     __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
-    __shared__ __align__(16) float s_acc[2][CHUNK * GS_REC_FLOATS];     // one private slot array per warp
-    __shared__ unsigned long long s_touched[2];                         // bit j: warp w wrote s_acc[w][j]
+    __shared__ __align__(16) float s_acc[NW][CHUNK * GS_REC_FLOATS];    // one private slot array per warp
+    __shared__ unsigned long long s_touched[NW];                        // bit j: warp w wrote s_acc[w][j]
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_max[2];
+    __shared__ uint32_t s_max[NW];
     __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cx = warp * 8 + (lane & 7), cy = lane >> 3;
+    const int cx = (warp & 1) * 8 + (lane & 7), cy = (warp >> 1) * (4 * PX) + (lane >> 3);
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t phases = 0u;
@@ -284,8 +292,7 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
 
     for (;;) {
         if (tid == 0) {
-            const unsigned i = atomicAdd(&p.status->q_bwd_heavy, 1u);
-            s_item = i < p.status->num_active ? (long long)p.active_tiles[i] : ITEM_DONE;
+            s_item = gs_active_tile(p, atomicAdd(&p.status->q_bwd_heavy, 1u));      // -1 == ITEM_DONE
         }
         __syncthreads();
         const long long item = s_item;
@@ -318,12 +325,17 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
             }
             tfbg[k] = T[k] * (b0 * g0[k] + b1 * g1[k] + b2 * g2[k]);             // T_final * (bg . dL/dC)
         }
-        uint32_t m = max(max(last[0], last[1]), max(last[2], last[3]));
+        uint32_t m = 0u;
+        #pragma unroll
+        for (int k = 0; k < PX; k++) m = max(m, last[k]);
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (lane == 0) s_max[warp] = m;
         __syncthreads();
-        const int nmax = (int)min(max(s_max[0], s_max[1]), (uint32_t)tc.n);
+        uint32_t mm = 0u;
+        #pragma unroll
+        for (int w = 0; w < NW; w++) mm = max(mm, s_max[w]);
+        const int nmax = (int)min(mm, (uint32_t)tc.n);
         if (nmax == 0) continue;                                // uniform; the next __syncthreads is after the fetch
 
         const int nchunks = (nmax + CHUNK - 1) / CHUNK;
@@ -430,14 +442,19 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
             }
             if (lane == 0) s_touched[warp] = touched;
             __syncthreads();
-            const unsigned long long t0 = s_touched[0], t1 = s_touched[1];
             for (int t = tid; t < cnt * 3; t += BT) {
                 const int j = t / 3, part = t - j * 3;
-                const bool a0 = (t0 >> j) & 1ull, a1 = (t1 >> j) & 1ull;
-                if (!(a0 || a1)) continue;
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a0) a = reinterpret_cast<const float4*>(s_acc[0])[t];
-                if (a1) { const float4 b = reinterpret_cast<const float4*>(s_acc[1])[t]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+                bool any = false;
+                #pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    if ((s_touched[w] >> j) & 1ull) {
+                        const float4 b = reinterpret_cast<const float4*>(s_acc[w])[t];
+                        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                        any = true;
+                    }
+                }
+                if (!any) continue;
                 if (part != 0) a.w = 0.f;                      // floats 7 and 11 of the record are never written
                 const int id = __float_as_int(rec[j * 3 + 2].w);
                 red_add_v4(gbase + (size_t)id * 3 + part, a);
@@ -456,16 +473,38 @@ int resident_ctas(const void* kernel, int block, int num_sms, int fallback_per_s
 
 }  // namespace
 
-void gs_launch_blend_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s)
+// pixels per thread for this launch: the caller's hint, else 4 (throughput-optimal for many tiles)
+static int pick_px(const GsParams& p) { return (p.blend_px == 1 || p.blend_px == 2) ? p.blend_px : 4; }
+
+template <int PX>
+static void launch_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s)
 {
     static thread_local int grid = 0, grid_sms = 0;
-    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_fwd_kernel, BT, num_sms, 16); grid_sms = num_sms; }
-    blend_fwd_kernel<<<grid, BT, 0, s>>>(p, color, depth, alpha);
+    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_fwd_kernel<PX>, 256 / PX, num_sms, 4 * PX); grid_sms = num_sms; }
+    blend_fwd_kernel<PX><<<grid, 256 / PX, 0, s>>>(p, color, depth, alpha);
+}
+template <int PX>
+static void launch_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms, cudaStream_t s)
+{
+    static thread_local int grid = 0, grid_sms = 0;
+    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_bwd_kernel<PX>, 256 / PX, num_sms, 2 * PX); grid_sms = num_sms; }
+    blend_bwd_kernel<PX><<<grid, 256 / PX, 0, s>>>(p, io);
+}
+
+void gs_launch_blend_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s)
+{
+    switch (pick_px(p)) {
+        case 1: launch_fwd<1>(p, color, depth, alpha, num_sms, s); break;
+        case 2: launch_fwd<2>(p, color, depth, alpha, num_sms, s); break;
+        default: launch_fwd<4>(p, color, depth, alpha, num_sms, s); break;
+    }
 }
 
 void gs_launch_blend_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms, cudaStream_t s)
 {
-    static thread_local int grid = 0, grid_sms = 0;
-    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_bwd_kernel, BT, num_sms, 8); grid_sms = num_sms; }
-    blend_bwd_kernel<<<grid, BT, 0, s>>>(p, io);
+    switch (pick_px(p)) {
+        case 1: launch_bwd<1>(p, io, num_sms, s); break;
+        case 2: launch_bwd<2>(p, io, num_sms, s); break;
+        default: launch_bwd<4>(p, io, num_sms, s); break;
+    }
 }

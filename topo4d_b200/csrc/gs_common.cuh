@@ -5,7 +5,8 @@
 //   tile_count    u32 [V*T + 1]                     instances per (view, tile)
 //   tile_start    u32 [V*T + 1]                     exclusive scan of tile_count; [V*T] = I
 //   tile_fill     u32 [V*T]                         scatter cursors
-//   active_tiles  u32 [V*T]                         compacted list of non-empty (view,tile) ids (order arbitrary)
+//   active_tiles  u32 [V*T]                         non-empty (view,tile) ids: long lists from the front, short ones
+//                                                   from the back (work queues hand out long tiles first)
 //   block_sums    u32 [scan blocks]                 scan scratch
 //   clamped       u8  [V*N]                         SH clamp bits (r,g,b)
 //   geom          48-byte record [V*N]              (x,y,conA,conB | conC,opacity,depth,thr | r,g,b,id)
@@ -36,13 +37,14 @@ struct GsStatusDev {
     int overflow;
     int max_tile_instances;
     // work queues of the persistent blend kernels (device-side dynamic scheduling)
-    unsigned int num_active;            // non-empty (view, tile) pairs listed in active_tiles[]
+    unsigned int num_long;              // non-empty tiles with >= GS_LONG_TILE instances: active_tiles[0 .. num_long)
     unsigned int q_fwd_heavy;           // next index into active_tiles[] (forward)
     unsigned int q_fwd_fill;            // next group of GS_FILL_GROUP tiles to background-fill (forward)
     unsigned int q_bwd_heavy;           // next index into active_tiles[] (backward)
     unsigned int q_sort;                // next index into active_tiles[] (sort + gather)
-    int pad[1];
+    unsigned int num_short;             // the other non-empty tiles: active_tiles[total_tiles-1 .. ] downwards
 };
+#define GS_LONG_TILE 384                // longest-first work order: long lists are handed out before short ones
 #define GS_FILL_GROUP 16
 
 struct GsLayout {
@@ -51,6 +53,7 @@ struct GsLayout {
     int tiles_x, tiles_y, tiles;        // per view
     long long total_tiles;              // V * tiles
     int scan_blocks;
+    int blend_px;                       // pixels per thread of the blend kernels (1, 2, 4; see gs_blend.cu)
 };
 
 #define GS_SCAN_ELEMS_PER_BLOCK 4096    // 1024 threads x 4
@@ -107,6 +110,7 @@ struct GsParams {
     uint32_t* n_contrib;
     float4* grad2d;
     int scan_blocks;
+    int blend_px;                       // pixels per thread of the blend kernels (1, 2, 4; see gs_blend.cu)
 };
 
 // launchers implemented in the kernel translation units
@@ -120,6 +124,16 @@ void gs_launch_blend_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms,
 void gs_launch_preprocess_bwd(const GsParams& p, const GsBackwardIO& io, cudaStream_t s);
 
 #ifdef __CUDACC__
+// i-th work item of the non-empty-tile queue (long tiles first), or -1 past the end
+__device__ __forceinline__ long long gs_active_tile(const GsParams& p, unsigned i)
+{
+    const unsigned nl = p.status->num_long, ns = p.status->num_short;
+    if (i < nl) return (long long)p.active_tiles[i];
+    const unsigned j = i - nl;
+    if (j < ns) return (long long)p.active_tiles[p.total_tiles - 1 - j];
+    return -1;
+}
+
 // ---- mbarrier + bulk async copy (TMA-family, SASS: UBLKCP / SYNCS) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

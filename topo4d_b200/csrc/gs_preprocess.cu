@@ -127,7 +127,22 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const GsParams p, int32
     float rgb[3];
     unsigned clampbits = 0;
     if (p.shs) {
-        const float* __restrict__ sh = p.shs + (size_t)i * p.M * 3;
+        // coefficients of the active bands into registers: 16-byte loads when a Gaussian's row is 16-byte aligned
+        const float* __restrict__ shg = p.shs + (size_t)i * p.M * 3;
+        const int nf = (p.deg + 1) * (p.deg + 1) * 3;
+        float sh[48];
+        if (((p.M * 3) & 3) == 0) {
+            const float4* __restrict__ sh4 = reinterpret_cast<const float4*>(shg);
+            #pragma unroll
+            for (int q = 0; q < 12; q++) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q * 4 < nf) t = __ldg(sh4 + q);
+                sh[4 * q] = t.x; sh[4 * q + 1] = t.y; sh[4 * q + 2] = t.z; sh[4 * q + 3] = t.w;
+            }
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 48; k++) sh[k] = k < nf ? __ldg(shg + k) : 0.f;
+        }
         const float dx = px - cam[GS_CAM_CAMPOS], dy = py - cam[GS_CAM_CAMPOS + 1], dz = pz - cam[GS_CAM_CAMPOS + 2];
         const float len = sqrtf(dx * dx + dy * dy + dz * dz);
         const float x = dx / len, y = dy / len, z = dz / len;

@@ -23,6 +23,16 @@ KERNELS_PER_FORWARD, KERNELS_PER_BACKWARD = 6, 2
 
 # remembered instance capacity per problem shape (grown on overflow)
 _CAP_MEMO: dict[tuple, int] = {}
+# remembered number of non-empty tiles per problem shape: picks the blend kernels' pixels-per-thread variant
+_ACTIVE_MEMO: dict[tuple, int] = {}
+
+
+def pick_blend_px(num_active_tiles: int | None) -> int:
+    """4 pixels/thread when there are enough non-empty tiles to fill the GPU (fewest instructions), 2 or 1 when
+    there are few (more warps per tile: the per-tile latency bounds such launches).  Never changes results."""
+    if num_active_tiles is None or num_active_tiles >= 4096:
+        return 4
+    return 2 if num_active_tiles >= 1800 else 1
 
 
 def _ptr(t: torch.Tensor | None):
@@ -65,6 +75,7 @@ class RasterState:
     use_sh: bool
     use_cov: bool
     device: torch.device
+    key: tuple = ()
     _status: GsStatus | None = field(default=None, repr=False)
 
     def status(self) -> GsStatus:
@@ -77,6 +88,8 @@ class RasterState:
             if code not in (_lib.GS_OK, _lib.GS_E_OVERFLOW):
                 _lib.check(code, "gs_read_status")
             self._status = st
+            if self.key:
+                _ACTIVE_MEMO[self.key] = int(st.num_active_tiles)
         return self._status
 
     def view(self) -> dict:
@@ -113,7 +126,7 @@ def _check_pairs(shs, colors_precomp, scales, rotations, cov3D_precomp):
 
 def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None, colors_precomp=None,
             scales=None, rotations=None, cov3D_precomp=None, sh_degree=0, scale_modifier=1.0, debug=False,
-            check="sync", cap_instances=None, stage_events=None):
+            check="sync", cap_instances=None, stage_events=None, blend_px=None):
     """Render V views.  `cameras`: [V,48] float32 CUDA tensor (see include/topo4d_b200.h GS_CAM_*).
 
     check: "sync"  -> read the status block after the launch (one small D2H, like upstream's
@@ -148,11 +161,12 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
 
     key = (N, V, H, W, dev.index)
     cap = int(cap_instances) if cap_instances is not None else _CAP_MEMO.get(key)
+    px = int(blend_px) if blend_px else pick_blend_px(_ACTIVE_MEMO.get(key))
 
     def make_problem(cap_):
         nbytes = L.gs_workspace_bytes(N, V, H, W, cap_)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        pr = GsProblem(N, V, H, W, int(sh_degree), M, float(scale_modifier), int(bool(debug)), cap_,
+        pr = GsProblem(N, V, H, W, int(sh_degree), M, float(scale_modifier), int(bool(debug)), px, 0, cap_,
                        _ptr(means3D), _ptr(shs), _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
                        _ptr(cov3D_precomp), _ptr(cameras), _ptr(ws), nbytes)
         return pr, ws
@@ -176,7 +190,7 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
                     e1.record()
                     stage_events.setdefault(name, []).append((e0, e1))
             state = RasterState(pr, ws, (means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, cameras),
-                                radii, N, V, H, W, M, shs is not None, cov3D_precomp is not None, dev)
+                                radii, N, V, H, W, M, shs is not None, cov3D_precomp is not None, dev, key)
             if check != "sync":
                 break
             st = state.status()
