@@ -25,7 +25,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 SOURCES = [
     ("gs_preprocess.cu", ["--fmad=false"]),
     ("gs_binning.cu", []),
-    ("gs_blend.cu", ["-DGS_PRECISE_EXP=1"]),   # expf (<= 1 ulp) on the blended pairs; =0 selects ex2.approx
+    ("gs_blend.cu", []),                       # -DGS_EXP_MODE=0|1|2 selects the exp flavour (default 2, see gs_blend.cu)
     ("gs_backward.cu", []),
     ("gs_api.cu", []),
     ("f3d_render.cu", ["--fmad=false"]),

@@ -33,6 +33,7 @@ static int validate(const GsProblem* p)
 {
     if (!p) return GS_E_BAD_ARGS;
     if (p->N < 0 || p->V < 1 || p->H < 1 || p->W < 1) return GS_E_BAD_ARGS;
+    if (p->N > 0x00ffffff) return GS_E_UNSUPPORTED;      // 24-bit Gaussian index inside the tile-sorted records
     if (p->cap_instances < 0 || p->cap_instances > 0x7fffffffLL) return GS_E_BAD_ARGS;
     if ((long long)p->V * p->N > 0x7fffffffLL) return GS_E_BAD_ARGS;
     if ((long long)p->V * ((p->W + GS_TILE - 1) / GS_TILE) * ((p->H + GS_TILE - 1) / GS_TILE) > 0x7fffffffLL) return GS_E_BAD_ARGS;

@@ -145,6 +145,11 @@ constexpr int SORT_SMEM_KEYS = 4096;   // 32 KB of 64-bit keys; longer lists are
 
 // Bitonic network in the "flip / disperse" form: every compare-exchange moves the smaller key to the
 // lower index, so virtual +inf padding above `n` never moves and arbitrary n needs no real padding.
+// A stage whose partner distance is <= 32 only moves keys inside 64-element windows that one warp owns (thread t
+// and its 31 warp mates cover pair indices of the same window in every such stage), so between two such stages a
+// __syncwarp() is enough; only stages that cross windows pay a __syncthreads().
+__device__ __forceinline__ void stage_sync(bool local) { if (local) __syncwarp(); else __syncthreads(); }
+
 template <typename KeyPtr>
 __device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nthreads)
 {
@@ -160,7 +165,8 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nt
                 if (a > b) { keys[i] = b; keys[j] = a; }
             }
         }
-        __syncthreads();
+        // next stage: jj = k/4 if it exists, else the flip of 2k
+        stage_sync(k <= 64 && ((k >> 2) > 0 ? true : (2 * k <= 64)));
         for (int jj = k >> 2; jj > 0; jj >>= 1) {
             for (int t = tid; t < (n2 >> 1); t += nthreads) {
                 const int i = ((t / jj) * (jj << 1)) + (t % jj), j = i + jj;
@@ -169,9 +175,45 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nt
                     if (a > b) { keys[i] = b; keys[j] = a; }
                 }
             }
-            __syncthreads();
+            const bool next_local = (jj >> 1) > 0 ? true : (2 * k <= 64);   // next is jj/2 (local if this one is) or flip(2k)
+            stage_sync(jj <= 32 && next_local);
         }
     }
+    __syncthreads();
+}
+
+// which of the tile's eight 8x4 pixel blocks can this splat reach at all?  Exact up to a safety margin: the minimum
+// of q(d) = 1/2 d^T conic d over the block's (continuous) rectangle against tau = -thr (thr already carries its own
+// margin).  q is convex, so the minimum is 0 if the centre is inside, else it lies on one of the four edges (a 1-D
+// clamped parabola each).  The blend kernels skip a block whose bit is clear without evaluating a single pixel; a
+// clear bit can never hide a contributor.
+__device__ __forceinline__ unsigned block_reach_mask(const float4 g0, const float4 g1, float tx0, float ty0)
+{
+    const float A = g0.z, B = g0.w, C = g1.x, tau = -g1.w;
+    if (!(A > 0.0f && C > 0.0f && A * C - B * B > 0.0f && tau < 3.0e38f)) return 0xffu;
+    if (!(tau >= 0.0f)) return 0u;
+    unsigned mask = 0u;
+    const float lim = tau * 1.0001f + 2.0e-3f;
+    const float nBC = -B / C, nBA = -B / A;
+    #pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const float bx0 = tx0 + 8.0f * (b & 1), by0 = ty0 + 4.0f * (b >> 1);
+        const float dx0 = g0.x - (bx0 + 7.0f), dx1 = g0.x - bx0;       // d = centre - pixel
+        const float dy0 = g0.y - (by0 + 3.0f), dy1 = g0.y - by0;
+        float qmin = 3.0e38f;
+        #pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float ex = e ? dx1 : dx0;                            // vertical edges: dx fixed
+            const float ty = fminf(fmaxf(nBC * ex, dy0), dy1);
+            qmin = fminf(qmin, 0.5f * (A * ex * ex + C * ty * ty) + B * ex * ty);
+            const float ey = e ? dy1 : dy0;                            // horizontal edges: dy fixed
+            const float tx = fminf(fmaxf(nBA * ey, dx0), dx1);
+            qmin = fminf(qmin, 0.5f * (A * tx * tx + C * ey * ey) + B * tx * ey);
+        }
+        if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) qmin = 0.0f;
+        if (qmin <= lim) mask |= 1u << b;
+    }
+    return mask;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParams p)
@@ -194,7 +236,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParam
         const int n = (int)(end - start);
         const int v = (int)(tg / p.tiles);
         unsigned long long* gk = p.pairs + start;
-        const unsigned long long* sorted;
+        unsigned long long* sorted;
         if (n <= SORT_SMEM_KEYS) {
             for (int t = tid; t < n; t += SORT_THREADS) s_keys[t] = gk[t];
             __syncthreads();
@@ -205,14 +247,29 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParam
             bitonic_sort(gk, n, tid, SORT_THREADS);     // in place in L2-resident global memory
             sorted = gk;
         }
-        // gather: 3 x 16 bytes per record, coalesced writes
         const float4* __restrict__ geom = p.geom + (size_t)v * p.N * 3;
         float4* __restrict__ rec = p.sorted_rec + start * 3;
+        const int tl = (int)(tg - (long long)v * p.tiles);
+        const float tx0 = (float)((tl % p.tiles_x) * GS_TILE), ty0 = (float)((tl / p.tiles_x) * GS_TILE);
+        // one thread per instance: Gaussian index out, block-reach mask into bits 24..31 of the key's low word
+        // (indices are < 2^24, validated on the host)
+        for (int k = tid; k < n; k += SORT_THREADS) {
+            const unsigned long long key = sorted[k];
+            const uint32_t id = (uint32_t)key & 0x00ffffffu;
+            p.sorted_ids[start + k] = id;
+            // only the PX = 1 / 2 blend variants read the mask (see gs_blend.cu)
+            const unsigned mask = (p.blend_px == 1 || p.blend_px == 2)
+                ? block_reach_mask(__ldg(geom + (size_t)id * 3), __ldg(geom + (size_t)id * 3 + 1), tx0, ty0) : 0xffu;
+            sorted[k] = key | ((unsigned long long)mask << 24);
+        }
+        __syncthreads();
+        // gather: 3 x 16 bytes per record, coalesced writes
         for (int t = tid; t < n * 3; t += SORT_THREADS) {
             const int k = t / 3, part = t - k * 3;
-            const uint32_t id = (uint32_t)(sorted[k] & 0xffffffffull);
-            rec[t] = __ldg(geom + (size_t)id * 3 + part);
-            if (part == 0) p.sorted_ids[start + k] = id;
+            const uint32_t low = (uint32_t)sorted[k];
+            float4 val = __ldg(geom + (size_t)(low & 0x00ffffffu) * 3 + part);
+            if (part == 2) val.w = __uint_as_float(low);           // id | reach mask << 24
+            rec[t] = val;
         }
         __syncthreads();   // s_keys is reused by the next tile
     }

@@ -53,14 +53,28 @@ __device__ __forceinline__ float splat_power(const ColTerms& r, float dy)
 {
     return __fmaf_rn(dy, __fmaf_rn(r.hC, dy, r.u), r.v);
 }
+// exp flavour (GS_EXP_MODE): 2 (default) = ex2.approx on a two-term product x*log2(e) with first-order correction,
+// ~2 ulp, 6 instructions; 1 = expf (<= 1 ulp, ~13 instructions); 0 = bare ex2.approx(x*log2e) (~8 ulp at |x| = 5,
+// 3 instructions -- breaks the 1e-3 gradient bar at opacity 1, kept for experiments only).
+#ifndef GS_EXP_MODE
+#define GS_EXP_MODE 2
+#endif
 __device__ __forceinline__ float splat_exp(float power)
 {
-#if defined(GS_PRECISE_EXP) && GS_PRECISE_EXP
+#if GS_EXP_MODE == 1
     return expf(power);
-#else
+#elif GS_EXP_MODE == 0
     float y = __fmul_rn(power, LOG2E), g;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(y));
     return g;
+#else
+    const float L2E_HI = 1.4426950216293335f, L2E_LO = 1.9259629911266175e-8f, LN2 = 0.6931471805599453f;
+    const float y = __fmul_rn(power, L2E_HI);
+    float r = __fmaf_rn(power, L2E_HI, -y);               // exact rounding error of the product
+    r = __fmaf_rn(power, L2E_LO, r);
+    float g;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(y));
+    return __fmaf_rn(g, __fmul_rn(r, LN2), g);            // 2^(y+r) = 2^y (1 + r ln2 + O(r^2)), |r| < 1e-6
 #endif
 }
 __device__ __forceinline__ float splat_alpha(float opacity, float G) { return fminf(GS_ALPHA_CAP, __fmul_rn(opacity, G)); }
@@ -125,6 +139,12 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cx = (warp & 1) * 8 + (lane & 7), cy = (warp >> 1) * (4 * PX) + (lane >> 3);   // comb: column cx, rows cy + 4k
     constexpr unsigned ALL = (1u << PX) - 1u;
+    constexpr unsigned BLK_MASK = PX == 4 ? 0x55u : (PX == 2 ? 0x5u : 0x1u);      // slot k <-> bit 2k after the shift
+    // The per-instance block-reach mask pays off when a warp owns few 8x4 blocks (PX 1, 2); at PX = 4 a warp owns half
+    // the tile, the mask is rarely empty and its bookkeeping costs more than it saves (measured), so it is ignored
+    // there (and the gather kernel does not compute it).
+    constexpr bool USE_MASK = PX < 4;
+    const unsigned blk_shift = 24u + (unsigned)(((warp >> 1) * PX) * 2 + (warp & 1));
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t phases = 0u;                       // bit b = parity to wait for on s_bar[b]
@@ -204,35 +224,42 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
             if (!__all_sync(0xffffffffu, done == ALL)) {
                 #pragma unroll 2
                 for (int j = 0; j < cnt; j++) {
-                    const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
-                    const ColTerms ct = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf));
-                    float pw[PX];
-                    unsigned pass = 0;
-                    #pragma unroll
-                    for (int k = 0; k < PX; k++) {
-                        pw[k] = splat_power(ct, __fsub_rn(r0.y, pyf[k]));
-                        if (pw[k] >= r1.w && pw[k] <= 0.0f) pass |= 1u << k;
-                    }
-                    pass &= ~done;
-                    if (pass) {
-                        const float4 r2 = rec[j * 3 + 2];
+                    // bits of the 8x4 blocks this warp's pixel slots live in (set by the gather kernel); warp-uniform
+                    const unsigned bm = USE_MASK ? (__float_as_uint(rec[j * 3 + 2].w) >> blk_shift) & BLK_MASK : BLK_MASK;
+                    if (bm != 0u) {
+                        const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
+                        const ColTerms ct = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf));
+                        float pw[PX];
+                        unsigned pass = 0;
                         #pragma unroll
                         for (int k = 0; k < PX; k++) {
-                            if (pass & (1u << k)) {
-                                const float alpha = splat_alpha(r1.y, splat_exp(pw[k]));
-                                const float test_T = next_T(T[k], alpha);
-                                const bool visible = alpha >= GS_ALPHA_MIN;
-                                const bool blend = visible && !(test_T < GS_T_MIN);
-                                if (visible && !blend) done |= 1u << k;
-                                if (blend) {
-                                    const float w = __fmul_rn(alpha, T[k]);
-                                    C0[k] = __fmaf_rn(r2.x, w, C0[k]);
-                                    C1[k] = __fmaf_rn(r2.y, w, C1[k]);
-                                    C2[k] = __fmaf_rn(r2.z, w, C2[k]);
-                                    D[k] = __fmaf_rn(r1.z, w, D[k]);
-                                    A[k] = __fadd_rn(A[k], w);
-                                    T[k] = test_T;
-                                    last[k] = (uint32_t)(c * CHUNK + j + 1);
+                            pw[k] = 0.f;
+                            if (bm & (1u << (2 * k))) {
+                                pw[k] = splat_power(ct, __fsub_rn(r0.y, pyf[k]));
+                                if (pw[k] >= r1.w && pw[k] <= 0.0f) pass |= 1u << k;
+                            }
+                        }
+                        pass &= ~done;
+                        if (pass) {
+                            const float4 r2 = rec[j * 3 + 2];
+                            #pragma unroll
+                            for (int k = 0; k < PX; k++) {
+                                if (pass & (1u << k)) {
+                                    const float alpha = splat_alpha(r1.y, splat_exp(pw[k]));
+                                    const float test_T = next_T(T[k], alpha);
+                                    const bool visible = alpha >= GS_ALPHA_MIN;
+                                    const bool blend = visible && !(test_T < GS_T_MIN);
+                                    if (visible && !blend) done |= 1u << k;
+                                    if (blend) {
+                                        const float w = __fmul_rn(alpha, T[k]);
+                                        C0[k] = __fmaf_rn(r2.x, w, C0[k]);
+                                        C1[k] = __fmaf_rn(r2.y, w, C1[k]);
+                                        C2[k] = __fmaf_rn(r2.z, w, C2[k]);
+                                        D[k] = __fmaf_rn(r1.z, w, D[k]);
+                                        A[k] = __fadd_rn(A[k], w);
+                                        T[k] = test_T;
+                                        last[k] = (uint32_t)(c * CHUNK + j + 1);
+                                    }
                                 }
                             }
                         }
@@ -266,9 +293,6 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
     }
 }
 
-// slot s of the butterfly -> float index inside the 12-float grad2d record
-__device__ __forceinline__ int slot_to_float(int s) { return s < 7 ? s : s + 1; }
-
 template <int PX>
 __global__ void __launch_bounds__(256 / PX)
 blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
@@ -276,6 +300,7 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
     constexpr int BT = 256 / PX, NW = 8 / PX;
     __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
     __shared__ __align__(16) float s_acc[NW][CHUNK * GS_REC_FLOATS];    // one private slot array per warp
+    __shared__ __align__(16) float s_tr[NW][32 * GS_REC_FLOATS];        // per-warp transpose scratch of the reduction
     __shared__ unsigned long long s_touched[NW];                        // bit j: warp w wrote s_acc[w][j]
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_max[NW];
@@ -286,8 +311,9 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
     __syncthreads();
     uint32_t phases = 0u;
     const size_t HW = (size_t)p.H * p.W;
-    const bool hi4 = lane & 16, hi3 = lane & 8, hi2 = lane & 4, hi1 = lane & 2;
-    const int my_slot = lane >> 1;
+    constexpr unsigned BLK_MASK = PX == 4 ? 0x55u : (PX == 2 ? 0x5u : 0x1u);
+    constexpr bool USE_MASK = PX < 4;
+    const unsigned blk_shift = 24u + (unsigned)(((warp >> 1) * PX) * 2 + (warp & 1));
     float* __restrict__ my_acc = s_acc[warp];
 
     for (;;) {
@@ -307,13 +333,14 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
         const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
 
         // per-pixel state: T (recovered back-to-front), suffix sums B of what lies behind, loss gradients
-        float pyf[PX], T[PX], B0[PX], B1[PX], B2[PX], Bd[PX], Ba[PX], g0[PX], g1[PX], g2[PX], gd[PX], ga[PX], tfbg[PX];
+        // Q[k] = g . (colour, depth, alpha accumulated BEHIND the current splat) + T_final (bg . g): because the loss
+        // gradients g are per-pixel constants the five suffix sums collapse into this one scalar.
+        float pyf[PX], T[PX], Q[PX], g0[PX], g1[PX], g2[PX], gd[PX], ga[PX];
         uint32_t last[PX];
         #pragma unroll
         for (int k = 0; k < PX; k++) {
             const int py = tc.ty0 + cy + 4 * k;
             pyf[k] = (float)py;
-            B0[k] = B1[k] = B2[k] = Bd[k] = Ba[k] = 0.f;
             T[k] = 0.f; last[k] = 0u; g0[k] = g1[k] = g2[k] = gd[k] = ga[k] = 0.f;
             if (px < p.W && py < p.H) {
                 const size_t pix = (size_t)py * p.W + px;
@@ -323,7 +350,7 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                 if (io.dL_ddepth) gd[k] = io.dL_ddepth[vb + pix];
                 if (io.dL_dalpha) ga[k] = io.dL_dalpha[vb + pix];
             }
-            tfbg[k] = T[k] * (b0 * g0[k] + b1 * g1[k] + b2 * g2[k]);             // T_final * (bg . dL/dC)
+            Q[k] = T[k] * (b0 * g0[k] + b1 * g1[k] + b2 * g2[k]);                // T_final * (bg . dL/dC)
         }
         uint32_t m = 0u;
         #pragma unroll
@@ -361,6 +388,8 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
             unsigned long long touched = 0ull;                  // warp-uniform
             for (int j = cnt - 1; j >= 0; j--) {
                 const uint32_t idx = (uint32_t)(c * CHUNK + j);
+                const unsigned bm = USE_MASK ? (__float_as_uint(rec[j * 3 + 2].w) >> blk_shift) & BLK_MASK : BLK_MASK;   // warp-uniform
+                if (USE_MASK && bm == 0u) continue;
                 const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
                 const float dx = __fsub_rn(r0.x, pxf);
                 const ColTerms ct = col_terms(r0.z, r0.w, r1.x, dx);
@@ -369,13 +398,16 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                 #pragma unroll
                 for (int k = 0; k < PX; k++) {
                     dyk[k] = __fsub_rn(r0.y, pyf[k]);
-                    pw[k] = splat_power(ct, dyk[k]);
-                    if (pw[k] >= r1.w && pw[k] <= 0.0f && idx < last[k]) pass |= 1u << k;
+                    pw[k] = 0.f;
+                    if (bm & (1u << (2 * k))) {
+                        pw[k] = splat_power(ct, dyk[k]);
+                        if (pw[k] >= r1.w && pw[k] <= 0.0f && idx < last[k]) pass |= 1u << k;
+                    }
                 }
                 if (!__any_sync(0xffffffffu, pass != 0u)) continue;
-                float r[16];
+                float r[10];
                 #pragma unroll
-                for (int s = 0; s < 16; s++) r[s] = 0.f;
+                for (int s = 0; s < 10; s++) r[s] = 0.f;
                 if (pass) {
                     const float4 r2 = rec[j * 3 + 2];
                     #pragma unroll
@@ -387,23 +419,17 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                                 const float ra = __fdividef(1.0f, __fsub_rn(1.0f, alpha));
                                 const float Tk = T[k] * ra;                      // undoes the forward's T*(1-alpha)
                                 const float w = __fmul_rn(alpha, Tk);
-                                // dL/dalpha_i = sum_ch (c_i T_i - B/(1-alpha_i)) g_ch  (+ depth, alpha, background terms)
-                                float dLda = (r2.x * Tk - B0[k] * ra) * g0[k] + (r2.y * Tk - B1[k] * ra) * g1[k] + (r2.z * Tk - B2[k] * ra) * g2[k];
-                                dLda += (r1.z * Tk - Bd[k] * ra) * gd[k];
-                                dLda += (Tk - Ba[k] * ra) * ga[k];
-                                dLda -= tfbg[k] * ra;
-                                B0[k] = __fmaf_rn(r2.x, w, B0[k]);
-                                B1[k] = __fmaf_rn(r2.y, w, B1[k]);
-                                B2[k] = __fmaf_rn(r2.z, w, B2[k]);
-                                Bd[k] = __fmaf_rn(r1.z, w, Bd[k]);
-                                Ba[k] = __fadd_rn(Ba[k], w);
-                                const float dL_dG = r1.y * dLda;                 // straight-through the 0.99 cap
-                                const float gdx = G * dx, gdy = G * dyk[k];
-                                r[0] += dL_dG * (-gdx * r0.z - gdy * r0.w);      // d/dpix.x
-                                r[1] += dL_dG * (-gdy * r1.x - gdx * r0.w);      // d/dpix.y
-                                r[2] += -0.5f * gdx * dx * dL_dG;                // d/dconA
-                                r[3] += -gdx * dyk[k] * dL_dG;                   // d/dconB (true, not halved)
-                                r[4] += -0.5f * gdy * dyk[k] * dL_dG;            // d/dconC
+                                // dL/dalpha_i = T_i (g . x_i) - (g . suffix_i + T_final bg.g) / (1 - alpha_i),  x_i = (rgb, depth, 1)
+                                const float Pk = __fmaf_rn(g0[k], r2.x, __fmaf_rn(g1[k], r2.y, __fmaf_rn(g2[k], r2.z, __fmaf_rn(gd[k], r1.z, ga[k]))));
+                                const float dLda = Tk * Pk - ra * Q[k];
+                                Q[k] = __fmaf_rn(w, Pk, Q[k]);
+                                const float sG = r1.y * dLda * G;                // dL/dG * G (straight-through the 0.99 cap)
+                                const float dy_ = dyk[k];
+                                r[0] += sG * (-dx * r0.z - dy_ * r0.w);          // d/dpix.x
+                                r[1] += sG * (-dy_ * r1.x - dx * r0.w);          // d/dpix.y
+                                r[2] += -0.5f * sG * dx * dx;                    // d/dconA
+                                r[3] += -sG * dx * dy_;                          // d/dconB (true, not halved)
+                                r[4] += -0.5f * sG * dy_ * dy_;                  // d/dconC
                                 r[5] += G * dLda;                                // d/dopacity
                                 r[6] += w * gd[k];                               // d/ddepth
                                 r[7] += w * g0[k]; r[8] += w * g1[k]; r[9] += w * g2[k];
@@ -412,32 +438,27 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                         }
                     }
                 }
-                // halving butterfly: afterwards lane pair (2s, 2s+1) holds the warp total of slot s
-                #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float send = hi4 ? r[i] : r[8 + i];
-                    const float keep = hi4 ? r[8 + i] : r[i];
-                    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
-                #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float send = hi3 ? r[i] : r[4 + i];
-                    const float keep = hi3 ? r[4 + i] : r[i];
-                    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                }
-                #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const float send = hi2 ? r[i] : r[2 + i];
-                    const float keep = hi2 ? r[2 + i] : r[i];
-                    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
+                // warp reduction through shared memory: every lane parks its 12-float partial record (three 16-byte
+                // stores, conflict-free), then lane (c, h) = (lane & 15, lane >> 4) sums column c over rows 2i+h
+                // (16 conflict-free loads) and one shuffle joins the halves: ~40 instructions instead of a 16-shuffle /
+                // 32-select butterfly (~70).
                 {
-                    const float send = hi1 ? r[0] : r[1];
-                    const float keep = hi1 ? r[1] : r[0];
-                    r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    float4* tr = reinterpret_cast<float4*>(s_tr[warp]);
+                    tr[lane * 3 + 0] = make_float4(r[0], r[1], r[2], r[3]);
+                    tr[lane * 3 + 1] = make_float4(r[4], r[5], r[6], 0.f);
+                    tr[lane * 3 + 2] = make_float4(r[7], r[8], r[9], 0.f);
+                    __syncwarp();
+                    const int c = lane & 15, h = lane >> 4;
+                    float acc = 0.f;
+                    if (c < GS_REC_FLOATS) {
+                        const float* col = s_tr[warp] + h * GS_REC_FLOATS + c;
+                        #pragma unroll
+                        for (int i = 0; i < 16; i++) acc += col[i * 2 * GS_REC_FLOATS];
+                    }
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                    if (h == 0 && c < GS_REC_FLOATS) my_acc[j * GS_REC_FLOATS + c] = acc;
+                    __syncwarp();
                 }
-                r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-                if (!(lane & 1) && my_slot < 10) my_acc[j * GS_REC_FLOATS + slot_to_float(my_slot)] = r[0];
                 touched |= 1ull << j;
             }
             if (lane == 0) s_touched[warp] = touched;
@@ -455,8 +476,7 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                     }
                 }
                 if (!any) continue;
-                if (part != 0) a.w = 0.f;                      // floats 7 and 11 of the record are never written
-                const int id = __float_as_int(rec[j * 3 + 2].w);
+                const int id = __float_as_int(rec[j * 3 + 2].w) & 0x00ffffff;
                 red_add_v4(gbase + (size_t)id * 3 + part, a);
             }
             __syncthreads();
