@@ -302,8 +302,19 @@ def run_ours(a):
             if k in stage_ms and stage_ms[k] > 0:
                 bw[k] = b / (stage_ms[k] * 1e-3) / 1e9
         dom = max(("blend_fwd", "blend_bwd"), key=lambda k: stage_ms.get(k, 0.0))
+        # measured DRAM traffic of the same kernel from the committed ncu capture (only valid for the same workload)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01e_traffic.json")))
+            w = tj["workload"]
+            if (w["views_per_launch"], w["width"], w["height"], w["gaussians"], w["sh_degree"], w["opacity"]) == \
+                    (vpl, a.width, a.height, a.gaussians, a.sh_degree, a.opacity):
+                traffic = tj["dram_bytes_per_launch"].get(dom + "_kernel")
+                traffic_src = tj["source"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": bw.get(dom), "peak": peak, "unit": "GB/s",
-                "frac": (bw.get(dom) or 0.0) / peak, "traffic": None, "peak_source": peak_src,
+                "frac": (bw.get(dom) or 0.0) / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom], "launch_ms": stage_ms.get(dom),
                 "N": a.gaussians, "I_per_launch": I_local, "P_per_launch": P_launch,
                 "all_stage_ms_per_launch": stage_ms, "stage_share_of_step": stage_share,
