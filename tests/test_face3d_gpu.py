@@ -81,4 +81,8 @@ def test_full_size_properties_8k():
         del ref
     u8 = mcc.image_to_u8_device(img)
     assert torch.equal(u8, (img * 255).to(torch.uint8))
+    # fused bake epilogue == reference's (render * 255).astype(np.uint8) (helpers.py:959) on a small mesh
+    vs, ts, cs = synth.uv_grid_mesh(grid=20, res=256, seed=2)
+    ref_small, _ = _cpu(vs, ts, cs, 256, 256, 3)
+    np.testing.assert_array_equal(f3d_render.render_colors_u8(vs, ts, cs, 256, 256, 3), (ref_small * 255).astype(np.uint8))
     assert float((img.sum(-1) != 0).float().mean()) > 0.95
