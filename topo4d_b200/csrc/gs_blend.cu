@@ -29,12 +29,18 @@
 
 namespace {
 
-// PX = pixels per thread (4, 2 or 1).  A tile is always 256 pixels, so a CTA has 256/PX threads = 8/PX warps;
+// PX = pixels per thread (8, 4, 2 or 1).  A tile is always 256 pixels, so a CTA has 256/PX threads = 8/PX warps;
 // warp w sits at columns 8*(w&1).. and rows (w>>1)*4*PX.., lane (lx,ly) owns pixels (8*(w&1)+lx, base+ly+4k).
+// PX = 8 is one warp per tile: lane (lx,ly) owns two columns (lx, lx+8) x four rows (ly+4k), slot k = column*4+row;
+// no __syncthreads between warps, one gradient reduction per (tile, Gaussian).
 // PX = 4 minimises instructions per (pixel, Gaussian) pair and is used when there are enough non-empty tiles
 // to fill the GPU; PX = 2 / 1 trade instructions for 2x / 4x more warps per tile when there are few tiles
 // (small scenes, one view per GPU): the per-tile latency, not the throughput, bounds those launches.
 constexpr int CHUNK = 64;                     // records per bulk copy (3 KB)
+#ifndef GS_FWD_UNROLL
+#define GS_FWD_UNROLL 2
+#endif
+constexpr int FWD_UNROLL = GS_FWD_UNROLL;
 constexpr uint32_t REC_BYTES = 48;
 [[maybe_unused]] constexpr float LOG2E = 1.4426950408889634f;
 
@@ -133,13 +139,14 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
                  float* __restrict__ out_alpha)
 {
     constexpr int BT = 256 / PX;
+    constexpr int NC = PX == 8 ? 2 : 1, NR = PX / NC;        // columns x rows of a thread's pixel comb; slot k = col*NR + row
     __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cx = (warp & 1) * 8 + (lane & 7), cy = (warp >> 1) * (4 * PX) + (lane >> 3);   // comb: column cx, rows cy + 4k
+    const int cx = (PX == 8 ? 0 : (warp & 1) * 8) + (lane & 7), cy = (PX == 8 ? 0 : (warp >> 1) * (4 * PX)) + (lane >> 3);
     constexpr unsigned ALL = (1u << PX) - 1u;
-    constexpr unsigned BLK_MASK = PX == 4 ? 0x55u : (PX == 2 ? 0x5u : 0x1u);      // slot k <-> bit 2k after the shift
+    constexpr unsigned BLK_MASK = PX == 8 ? 0x5555u : (PX == 4 ? 0x55u : (PX == 2 ? 0x5u : 0x1u));   // slot k <-> bit 2k after the shift
     // The per-instance block-reach mask pays off when a warp owns few 8x4 blocks (PX 1, 2); at PX = 4 a warp owns half
     // the tile, the mask is rarely empty and its bookkeeping costs more than it saves (measured), so it is ignored
     // there (and the gather kernel does not compute it).
@@ -186,17 +193,17 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
 
         // ---- one non-empty tile ----
         const TileCtx tc = tile_ctx(p, item);
-        const int px = tc.tx0 + cx;
-        const float pxf = (float)px;
-        float pyf[PX], T[PX], C0[PX], C1[PX], C2[PX], D[PX], A[PX];
+        float pxf[NC], pyf[NR], T[PX], C0[PX], C1[PX], C2[PX], D[PX], A[PX];
         uint32_t last[PX];
         unsigned done = 0;                                      // bit k: pixel k finished (or outside)
         #pragma unroll
+        for (int c2 = 0; c2 < NC; c2++) pxf[c2] = (float)(tc.tx0 + cx + 8 * c2);
+        #pragma unroll
+        for (int k4 = 0; k4 < NR; k4++) pyf[k4] = (float)(tc.ty0 + cy + 4 * k4);
+        #pragma unroll
         for (int k = 0; k < PX; k++) {
-            const int py = tc.ty0 + cy + 4 * k;
-            pyf[k] = (float)py;
             T[k] = 1.f; C0[k] = C1[k] = C2[k] = D[k] = A[k] = 0.f; last[k] = 0u;
-            if (px >= p.W || py >= p.H) done |= 1u << k;
+            if (tc.tx0 + cx + 8 * (k / NR) >= p.W || tc.ty0 + cy + 4 * (k % NR) >= p.H) done |= 1u << k;
         }
         const unsigned outside = done;
         const int nchunks = (tc.n + CHUNK - 1) / CHUNK;
@@ -222,21 +229,25 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
             // warp re-converges every record.  Leaving the loop from inside the divergent blend block makes the
             // compiler re-converge only at loop exit, which serialises the 32 lanes (measured: 12x slower).
             if (!__all_sync(0xffffffffu, done == ALL)) {
-                #pragma unroll 2
+                #pragma unroll FWD_UNROLL
                 for (int j = 0; j < cnt; j++) {
                     // bits of the 8x4 blocks this warp's pixel slots live in (set by the gather kernel); warp-uniform
                     const unsigned bm = USE_MASK ? (__float_as_uint(rec[j * 3 + 2].w) >> blk_shift) & BLK_MASK : BLK_MASK;
                     if (bm != 0u) {
                         const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
-                        const ColTerms ct = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf));
-                        float pw[PX];
+                        ColTerms ct[NC];
+                        float dyr[NR], pw[PX];
+                        #pragma unroll
+                        for (int c2 = 0; c2 < NC; c2++) ct[c2] = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf[c2]));
+                        #pragma unroll
+                        for (int k4 = 0; k4 < NR; k4++) dyr[k4] = __fsub_rn(r0.y, pyf[k4]);
                         unsigned pass = 0;
                         #pragma unroll
                         for (int k = 0; k < PX; k++) {
                             pw[k] = 0.f;
                             if (bm & (1u << (2 * k))) {
-                                pw[k] = splat_power(ct, __fsub_rn(r0.y, pyf[k]));
-                                if (pw[k] >= r1.w && pw[k] <= 0.0f) pass |= 1u << k;
+                                pw[k] = splat_power(ct[k / NR], dyr[k % NR]);
+                                if (pw[k] >= r1.w) pass |= 1u << k;          // the (rare) power > 0 skip is tested on the blend path
                             }
                         }
                         pass &= ~done;
@@ -247,7 +258,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
                                 if (pass & (1u << k)) {
                                     const float alpha = splat_alpha(r1.y, splat_exp(pw[k]));
                                     const float test_T = next_T(T[k], alpha);
-                                    const bool visible = alpha >= GS_ALPHA_MIN;
+                                    const bool visible = alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f;
                                     const bool blend = visible && !(test_T < GS_T_MIN);
                                     if (visible && !blend) done |= 1u << k;
                                     if (blend) {
@@ -280,7 +291,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
             #pragma unroll
             for (int k = 0; k < PX; k++) {
                 if (outside & (1u << k)) continue;
-                const size_t pix = (size_t)(tc.ty0 + cy + 4 * k) * p.W + px;
+                const size_t pix = (size_t)(tc.ty0 + cy + 4 * (k % NR)) * p.W + (tc.tx0 + cx + 8 * (k / NR));
                 p.final_T[vb + pix] = T[k];
                 p.n_contrib[vb + pix] = last[k];
                 out_color[vb * 3 + pix] = __fmaf_rn(T[k], b0, C0[k]);
@@ -297,7 +308,8 @@ template <int PX>
 __global__ void __launch_bounds__(256 / PX)
 blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
 {
-    constexpr int BT = 256 / PX, NW = 8 / PX;
+    constexpr int BT = 256 / PX, NW = PX == 8 ? 1 : 8 / PX;
+    constexpr int NC = PX == 8 ? 2 : 1, NR = PX / NC;
     __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
     __shared__ __align__(16) float s_acc[NW][CHUNK * GS_REC_FLOATS];    // one private slot array per warp
     __shared__ __align__(16) float s_tr[NW][32 * GS_REC_FLOATS];        // per-warp transpose scratch of the reduction
@@ -306,12 +318,12 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
     __shared__ uint32_t s_max[NW];
     __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cx = (warp & 1) * 8 + (lane & 7), cy = (warp >> 1) * (4 * PX) + (lane >> 3);
+    const int cx = (PX == 8 ? 0 : (warp & 1) * 8) + (lane & 7), cy = (PX == 8 ? 0 : (warp >> 1) * (4 * PX)) + (lane >> 3);
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t phases = 0u;
     const size_t HW = (size_t)p.H * p.W;
-    constexpr unsigned BLK_MASK = PX == 4 ? 0x55u : (PX == 2 ? 0x5u : 0x1u);
+    constexpr unsigned BLK_MASK = PX == 8 ? 0x5555u : (PX == 4 ? 0x55u : (PX == 2 ? 0x5u : 0x1u));
     constexpr bool USE_MASK = PX < 4;
     const unsigned blk_shift = 24u + (unsigned)(((warp >> 1) * PX) * 2 + (warp & 1));
     float* __restrict__ my_acc = s_acc[warp];
@@ -326,8 +338,6 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
         if (item == ITEM_DONE) break;
 
         const TileCtx tc = tile_ctx(p, item);
-        const int px = tc.tx0 + cx;
-        const float pxf = (float)px;
         const size_t vb = (size_t)tc.v * HW;
         const float* __restrict__ bg = p.cams + (size_t)tc.v * GS_CAM_FLOATS + GS_CAM_BG;
         const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
@@ -335,12 +345,15 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
         // per-pixel state: T (recovered back-to-front), suffix sums B of what lies behind, loss gradients
         // Q[k] = g . (colour, depth, alpha accumulated BEHIND the current splat) + T_final (bg . g): because the loss
         // gradients g are per-pixel constants the five suffix sums collapse into this one scalar.
-        float pyf[PX], T[PX], Q[PX], g0[PX], g1[PX], g2[PX], gd[PX], ga[PX];
+        float pxf[NC], pyf[NR], T[PX], Q[PX], g0[PX], g1[PX], g2[PX], gd[PX], ga[PX];
         uint32_t last[PX];
         #pragma unroll
+        for (int c2 = 0; c2 < NC; c2++) pxf[c2] = (float)(tc.tx0 + cx + 8 * c2);
+        #pragma unroll
+        for (int k4 = 0; k4 < NR; k4++) pyf[k4] = (float)(tc.ty0 + cy + 4 * k4);
+        #pragma unroll
         for (int k = 0; k < PX; k++) {
-            const int py = tc.ty0 + cy + 4 * k;
-            pyf[k] = (float)py;
+            const int px = tc.tx0 + cx + 8 * (k / NR), py = tc.ty0 + cy + 4 * (k % NR);
             T[k] = 0.f; last[k] = 0u; g0[k] = g1[k] = g2[k] = gd[k] = ga[k] = 0.f;
             if (px < p.W && py < p.H) {
                 const size_t pix = (size_t)py * p.W + px;
@@ -391,17 +404,19 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                 const unsigned bm = USE_MASK ? (__float_as_uint(rec[j * 3 + 2].w) >> blk_shift) & BLK_MASK : BLK_MASK;   // warp-uniform
                 if (USE_MASK && bm == 0u) continue;
                 const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
-                const float dx = __fsub_rn(r0.x, pxf);
-                const ColTerms ct = col_terms(r0.z, r0.w, r1.x, dx);
-                float pw[PX], dyk[PX];
+                ColTerms ct[NC];
+                float dxc[NC], dyr[NR], pw[PX];
+                #pragma unroll
+                for (int c2 = 0; c2 < NC; c2++) { dxc[c2] = __fsub_rn(r0.x, pxf[c2]); ct[c2] = col_terms(r0.z, r0.w, r1.x, dxc[c2]); }
+                #pragma unroll
+                for (int k4 = 0; k4 < NR; k4++) dyr[k4] = __fsub_rn(r0.y, pyf[k4]);
                 unsigned pass = 0;
                 #pragma unroll
                 for (int k = 0; k < PX; k++) {
-                    dyk[k] = __fsub_rn(r0.y, pyf[k]);
                     pw[k] = 0.f;
                     if (bm & (1u << (2 * k))) {
-                        pw[k] = splat_power(ct, dyk[k]);
-                        if (pw[k] >= r1.w && pw[k] <= 0.0f && idx < last[k]) pass |= 1u << k;
+                        pw[k] = splat_power(ct[k / NR], dyr[k % NR]);
+                        if (pw[k] >= r1.w && idx < last[k]) pass |= 1u << k;  // the (rare) power > 0 skip is tested on the blend path
                     }
                 }
                 if (!__any_sync(0xffffffffu, pass != 0u)) continue;
@@ -415,7 +430,7 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                         if (pass & (1u << k)) {
                             const float G = splat_exp(pw[k]);
                             const float alpha = splat_alpha(r1.y, G);
-                            if (alpha >= GS_ALPHA_MIN) {
+                            if (alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f) {
                                 const float ra = __fdividef(1.0f, __fsub_rn(1.0f, alpha));
                                 const float Tk = T[k] * ra;                      // undoes the forward's T*(1-alpha)
                                 const float w = __fmul_rn(alpha, Tk);
@@ -424,7 +439,7 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                                 const float dLda = Tk * Pk - ra * Q[k];
                                 Q[k] = __fmaf_rn(w, Pk, Q[k]);
                                 const float sG = r1.y * dLda * G;                // dL/dG * G (straight-through the 0.99 cap)
-                                const float dy_ = dyk[k];
+                                const float dx = dxc[k / NR], dy_ = dyr[k % NR];
                                 r[0] += sG * (-dx * r0.z - dy_ * r0.w);          // d/dpix.x
                                 r[1] += sG * (-dy_ * r1.x - dx * r0.w);          // d/dpix.y
                                 r[2] += -0.5f * sG * dx * dx;                    // d/dconA
@@ -494,7 +509,7 @@ int resident_ctas(const void* kernel, int block, int num_sms, int fallback_per_s
 }  // namespace
 
 // pixels per thread for this launch: the caller's hint, else 4 (throughput-optimal for many tiles)
-static int pick_px(const GsParams& p) { return (p.blend_px == 1 || p.blend_px == 2) ? p.blend_px : 4; }
+static int pick_px(const GsParams& p) { return (p.blend_px == 1 || p.blend_px == 2 || p.blend_px == 8) ? p.blend_px : 4; }
 
 template <int PX>
 static void launch_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s)
@@ -516,6 +531,7 @@ void gs_launch_blend_fwd(const GsParams& p, float* color, float* depth, float* a
     switch (pick_px(p)) {
         case 1: launch_fwd<1>(p, color, depth, alpha, num_sms, s); break;
         case 2: launch_fwd<2>(p, color, depth, alpha, num_sms, s); break;
+        case 8: launch_fwd<8>(p, color, depth, alpha, num_sms, s); break;
         default: launch_fwd<4>(p, color, depth, alpha, num_sms, s); break;
     }
 }
@@ -525,6 +541,7 @@ void gs_launch_blend_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms,
     switch (pick_px(p)) {
         case 1: launch_bwd<1>(p, io, num_sms, s); break;
         case 2: launch_bwd<2>(p, io, num_sms, s); break;
+        case 8: launch_bwd<8>(p, io, num_sms, s); break;
         default: launch_bwd<4>(p, io, num_sms, s); break;
     }
 }
