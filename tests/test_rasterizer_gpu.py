@@ -157,3 +157,31 @@ def test_blend_px_variants_agree():
         g = engine.backward(out[4], gc, gd, ga).flat
         assert torch.allclose(g, gref, rtol=2e-4, atol=2e-5 * float(gref.abs().max())), px
     assert engine.pick_blend_px(None) == 4 and engine.pick_blend_px(10000) == 4 and engine.pick_blend_px(2000) == 2 and engine.pick_blend_px(300) == 1
+
+
+def test_very_long_tile_lists_use_the_global_sort_path():
+    """Every tile list longer than the 4096-key shared-memory sort: in-place global bitonic sort, dozens of 64-record
+    chunks per tile, early termination deep inside the list."""
+    rng = np.random.default_rng(31)
+    n = 5200
+    scene = dict(means3D=(rng.normal(0, 0.05, (n, 3))).astype(np.float32),
+                 scales=np.full((n, 3), 0.6, np.float32) * rng.uniform(0.8, 1.2, (n, 3)).astype(np.float32),
+                 rotations=np.tile(np.array([[1, 0, 0, 0]], np.float32), (n, 1)),
+                 opacities=rng.uniform(0.004, 0.05, (n, 1)).astype(np.float32),
+                 colors_precomp=rng.uniform(0, 1, (n, 3)).astype(np.float32))
+    cam = synth.front_camera(48, 40, dist=4.0, fx=48.0)
+    m = parity.compare(scene, [cam], 40, 48, 0, (0.1, 0.2, 0.3))
+    assert m["num_rendered"] == n * 9          # 3 x 3 tiles, every splat covers them all
+    parity.assert_parity(m, allow_flips=2)
+
+
+def test_odd_width_and_degenerate_inputs():
+    """W % 4 != 0 (scalar store path), zero / negative opacity, a splat with a NaN mean (culled), huge splat."""
+    scene = synth.random_scene(1500, seed=33)
+    scene["opacities"][:50] = 0.0
+    scene["opacities"][50:60] = -0.5
+    scene["means3D"][60] = np.nan
+    scene["scales"][61] = 50.0
+    cam = synth.make_camera(synth.look_at((0.5, 0.2, -3.0)), 131, 77, 120.0, 110.0)
+    m = parity.compare(scene, [cam], 77, 131, 0, (0.3, 0.3, 0.3))
+    parity.assert_parity(m, allow_flips=2)

@@ -39,7 +39,7 @@ __device__ __forceinline__ Rect tile_rect(float pix_x, float pix_y, float radius
     return r;
 }
 
-__global__ void __launch_bounds__(256) preprocess_kernel(const GsParams p, int32_t* __restrict__ radii)
+__global__ void __launch_bounds__(256, 3) preprocess_kernel(const GsParams p, int32_t* __restrict__ radii)
 {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)p.V * p.N) return;
