@@ -80,3 +80,30 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises(RuntimeError, match="CUDA-only"):
         Renderer(raster_settings=_settings(cam, (0, 0, 0)))(means3D=t["means3D"], means2D=None, opacities=t["opacities"],
                                                             colors_precomp=t["colors_precomp"], scales=t["scales"], rotations=t["rotations"])
+
+
+def test_async_mode_defers_the_overflow_check(monkeypatch):
+    """TOPO4D_B200_SYNC=0: no host sync per forward; an overflow of call k surfaces at call k+1 and the retry works."""
+    from diff_gaussian_rasterization import GaussianRasterizer as Renderer
+    from topo4d_b200 import engine, rasterizer
+    monkeypatch.setenv("TOPO4D_B200_SYNC", "0")
+    rasterizer._PENDING.clear()
+    sc = synth.random_scene(1777, seed=5)
+    cam = synth.front_camera(112, 80)
+    t = {k: torch.tensor(v, device="cuda") for k, v in sc.items()}
+    r = Renderer(raster_settings=_settings(cam, (0, 0, 0)))
+
+    def call(scale):
+        return r(means3D=t["means3D"], means2D=torch.zeros_like(t["means3D"]), opacities=t["opacities"],
+                 colors_precomp=t["colors_precomp"], scales=t["scales"] * scale, rotations=t["rotations"])
+    small = call(0.2)[0].clone()                       # sizes the workspace for few instances (first call counts exactly)
+    call(6.0)                                          # needs far more instances than the remembered capacity: overflows silently
+    with pytest.raises(RuntimeError, match="capacity has been raised"):
+        call(0.2)
+    big = call(6.0)[0]                                 # retry with the raised capacity
+    call(0.2)                                          # would raise if `big` had overflowed again
+    ref, _ = parity.run_oracle(dict(sc, scales=sc["scales"] * 6.0), [cam], 80, 112, 0, (0, 0, 0))
+    assert np.abs(big.cpu().numpy() - ref[0]["color"]).max() <= parity.ABS_TOL
+    ref_s, _ = parity.run_oracle(dict(sc, scales=sc["scales"] * 0.2), [cam], 80, 112, 0, (0, 0, 0))
+    assert np.abs(small.cpu().numpy() - ref_s[0]["color"]).max() <= parity.ABS_TOL
+    rasterizer._PENDING.clear()

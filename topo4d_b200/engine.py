@@ -25,6 +25,19 @@ KERNELS_PER_FORWARD, KERNELS_PER_BACKWARD = 6, 2
 _CAP_MEMO: dict[tuple, int] = {}
 # remembered number of non-empty tiles per problem shape: picks the blend kernels' pixels-per-thread variant
 _ACTIVE_MEMO: dict[tuple, int] = {}
+_WS_BYTES: dict[tuple, int] = {}
+ctypes_sizeof_status_dev = 48      # sizeof(GsStatusDev), csrc/gs_common.cuh (layout mirrored in RasterState.status)
+_PINNED_RING = None                # one pinned allocation, 256 status slots handed out round-robin
+_PINNED_NEXT = 0
+
+
+def _pinned_slot() -> torch.Tensor:
+    global _PINNED_RING, _PINNED_NEXT
+    if _PINNED_RING is None:
+        _PINNED_RING = torch.empty(256 * 64, dtype=torch.uint8).pin_memory()
+    i = _PINNED_NEXT
+    _PINNED_NEXT = (i + 1) % 256
+    return _PINNED_RING[i * 64:i * 64 + ctypes_sizeof_status_dev]
 
 
 def pick_blend_px(num_active_tiles: int | None) -> int:
@@ -42,9 +55,9 @@ def _ptr(t: torch.Tensor | None):
 def _f32c(t: torch.Tensor | None, dev) -> torch.Tensor | None:
     if t is None:
         return None
-    if t.dtype != torch.float32 or t.device != dev:
-        t = t.to(device=dev, dtype=torch.float32)
-    return t.contiguous()
+    if t.dtype is torch.float32 and t.device == dev:
+        return t if t.is_contiguous() else t.contiguous()
+    return t.to(device=dev, dtype=torch.float32).contiguous()
 
 
 def pack_cameras_numpy(cams, bg=(0.0, 0.0, 0.0)) -> np.ndarray:
@@ -77,9 +90,31 @@ class RasterState:
     device: torch.device
     key: tuple = ()
     _status: GsStatus | None = field(default=None, repr=False)
+    _status_pinned: torch.Tensor | None = field(default=None, repr=False)     # async copy of the status block ...
+    _status_event: torch.cuda.Event | None = field(default=None, repr=False)  # ... complete once this event has fired
+
+    def prefetch_status(self) -> None:
+        """Enqueue an asynchronous copy of the status block into pinned memory right behind the forward: a later
+        status() then only waits for THAT point of the stream, not for whatever was queued afterwards."""
+        self._status_pinned = _pinned_slot()
+        self._status_pinned.copy_(self.workspace[:ctypes_sizeof_status_dev], non_blocking=True)
+        self._status_event = torch.cuda.Event()
+        self._status_event.record(torch.cuda.current_stream(self.device))
 
     def status(self) -> GsStatus:
         """Synchronising read of the device status block (num_rendered, overflow, longest tile list)."""
+        if self._status is None and self._status_pinned is not None:
+            self._status_event.synchronize()
+            raw = self._status_pinned.numpy()
+            st = GsStatus()
+            st.num_instances = int(raw[0:8].view("<i8")[0])
+            st.cap_instances = int(raw[8:16].view("<i8")[0])
+            st.overflow = int(raw[16:20].view("<i4")[0])
+            st.max_tile_instances = int(raw[20:24].view("<i4")[0])
+            st.num_active_tiles = int(raw[24:28].view("<u4")[0]) + int(raw[44:48].view("<u4")[0])   # num_long + num_short
+            self._status = st
+            if self.key:
+                _ACTIVE_MEMO[self.key] = int(st.num_active_tiles)
         if self._status is None:
             st = GsStatus()
             with torch.cuda.device(self.device):
@@ -131,7 +166,9 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
 
     check: "sync"  -> read the status block after the launch (one small D2H, like upstream's
                       num_rendered read) and transparently re-run with a larger capacity on overflow;
-           "none"  -> fully asynchronous; call ``state.status()`` later to validate.
+           "none"  -> fully asynchronous; call ``state.status()`` later to validate (synchronises the stream);
+           "deferred" -> asynchronous, and the status block is copied to pinned memory right behind the forward
+                      so that a later ``state.status()`` waits for this forward only.
     stage_events: optional dict; when given, the pipeline is issued one stage at a time
            (gs_forward_stages) with CUDA events recorded around every stage on the current stream
            and appended to stage_events[stage_name] as (start, end) pairs.
@@ -153,9 +190,12 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
     M = 0 if shs is None else int(shs.reshape(N, -1, 3).shape[1]) if N > 0 else int(shs.shape[1])
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
-    color = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev)
-    depth = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
-    alpha = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
+    # one allocation for the three images (each stays a contiguous tensor of its own shape)
+    P = H * W
+    imgs = torch.empty(V * 5 * P, dtype=torch.float32, device=dev)
+    color = imgs[:V * 3 * P].view(V, 3, H, W)
+    depth = imgs[V * 3 * P:V * 4 * P].view(V, 1, H, W)
+    alpha = imgs[V * 4 * P:].view(V, 1, H, W)
     radii = torch.empty((V, max(N, 1)), dtype=torch.int32, device=dev)
     out = GsForwardOut(_ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii))
 
@@ -164,7 +204,10 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
     px = int(blend_px) if blend_px else pick_blend_px(_ACTIVE_MEMO.get(key))
 
     def make_problem(cap_):
-        nbytes = L.gs_workspace_bytes(N, V, H, W, cap_)
+        wk = (N, V, H, W, cap_)
+        nbytes = _WS_BYTES.get(wk)
+        if nbytes is None:
+            nbytes = _WS_BYTES[wk] = L.gs_workspace_bytes(N, V, H, W, cap_)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         pr = GsProblem(N, V, H, W, int(sh_degree), M, float(scale_modifier), int(bool(debug)), px, 0, cap_,
                        _ptr(means3D), _ptr(shs), _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
@@ -177,7 +220,7 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
             pr, ws = make_problem(0)
             n = C.c_int64(0)
             _lib.check(L.gs_count_instances(C.byref(pr), C.byref(n), stream), "gs_count_instances")
-            cap = int(n.value * 1.25) + 4096
+            cap = int(n.value * (1.25 if check == "sync" else 2.0)) + 4096
         while True:
             pr, ws = make_problem(cap)
             if stage_events is None:
@@ -191,6 +234,8 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
                     stage_events.setdefault(name, []).append((e0, e1))
             state = RasterState(pr, ws, (means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, cameras),
                                 radii, N, V, H, W, M, shs is not None, cov3D_precomp is not None, dev, key)
+            if check == "deferred":
+                state.prefetch_status()
             if check != "sync":
                 break
             st = state.status()

@@ -10,6 +10,7 @@ Adds ``render_views`` -- the same op over V cameras in one launch sequence (view
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import NamedTuple
 
@@ -61,16 +62,43 @@ def pack_settings(rs: GaussianRasterizationSettings) -> torch.Tensor:
     return packed
 
 
+# TOPO4D_B200_SYNC=1 (default): read the device status block after every forward -- one small D2H, exactly the
+# host sync upstream does for `num_rendered` -- and transparently re-run if the instance capacity overflowed.
+# TOPO4D_B200_SYNC=0: fully asynchronous forward; the status of call k is checked at call k+1 (by then it is
+# long complete, so the check is free) and an overflow raises there after growing the capacity for the retry.
+_PENDING: list = []
+
+
+def _sync_mode() -> bool:
+    return os.environ.get("TOPO4D_B200_SYNC", "1") != "0"
+
+
+def _check_pending():
+    while _PENDING:
+        st = _PENDING.pop()
+        s = st.status()
+        if s.overflow:
+            engine._CAP_MEMO[st.key] = int(s.num_instances * 1.5) + 4096
+            raise RuntimeError("topo4d_b200: the previous asynchronous render needed %d (tile, Gaussian) instances but its "
+                               "workspace held %d; its images were incomplete.  The capacity has been raised -- re-run "
+                               "that step (or use TOPO4D_B200_SYNC=1)." % (s.num_instances, s.cap_instances))
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     """V-view op.  Outputs carry the leading V dimension; the single-view wrapper strips it."""
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 cameras, image_height, image_width, sh_degree, scale_modifier, debug):
+        sync = _sync_mode()
+        if not sync:
+            _check_pending()
         color, radii, depth, alpha, state = engine.forward(
             means3D, opacities, cameras, image_height, image_width, shs=sh, colors_precomp=colors_precomp,
             scales=scales, rotations=rotations, cov3D_precomp=cov3Ds_precomp, sh_degree=sh_degree,
-            scale_modifier=scale_modifier, debug=debug, check="sync")
+            scale_modifier=scale_modifier, debug=debug, check="sync" if sync else "deferred")
+        if not sync:
+            _PENDING.append(state)
         ctx.state = state
         ctx.shapes = tuple(None if t is None else t.shape for t in
                            (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
