@@ -155,11 +155,14 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nt
 {
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
-    for (int k = 2; k <= n2; k <<= 1) {
+    const int half = n2 >> 1;
+    // every block size / partner distance is a power of two: index arithmetic is shifts and masks only
+    for (int lk = 1; (1 << lk) <= n2; lk++) {
+        const int k = 1 << lk, hk = k >> 1;
         // flip: partner is the mirror position inside the k-block
-        for (int t = tid; t < (n2 >> 1); t += nthreads) {
-            const int blk = t / (k >> 1), off = t % (k >> 1);
-            const int i = blk * k + off, j = blk * k + (k - 1 - off);
+        for (int t = tid; t < half; t += nthreads) {
+            const int blk = t >> (lk - 1), off = t & (hk - 1);
+            const int i = (blk << lk) + off, j = (blk << lk) + (k - 1 - off);
             if (j < n) {
                 const unsigned long long a = keys[i], b = keys[j];
                 if (a > b) { keys[i] = b; keys[j] = a; }
@@ -167,15 +170,16 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nt
         }
         // next stage: jj = k/4 if it exists, else the flip of 2k
         stage_sync(k <= 64 && ((k >> 2) > 0 ? true : (2 * k <= 64)));
-        for (int jj = k >> 2; jj > 0; jj >>= 1) {
-            for (int t = tid; t < (n2 >> 1); t += nthreads) {
-                const int i = ((t / jj) * (jj << 1)) + (t % jj), j = i + jj;
+        for (int lj = lk - 2; lj >= 0; lj--) {
+            const int jj = 1 << lj;
+            for (int t = tid; t < half; t += nthreads) {
+                const int i = ((t >> lj) << (lj + 1)) + (t & (jj - 1)), j = i + jj;
                 if (j < n) {
                     const unsigned long long a = keys[i], b = keys[j];
                     if (a > b) { keys[i] = b; keys[j] = a; }
                 }
             }
-            const bool next_local = (jj >> 1) > 0 ? true : (2 * k <= 64);   // next is jj/2 (local if this one is) or flip(2k)
+            const bool next_local = lj > 0 ? true : (2 * k <= 64);   // next is jj/2 (local if this one is) or flip(2k)
             stage_sync(jj <= 32 && next_local);
         }
     }
