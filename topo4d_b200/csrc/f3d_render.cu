@@ -121,9 +121,13 @@ f3d_pass1_kernel(const float* __restrict__ vertices, const int* __restrict__ tri
             const int sbw = __shfl_sync(0xffffffffu, bw, src);
             const int sarea = __shfl_sync(0xffffffffu, area, src);
             const int sidx = (int)base + src;
+            // lanes walk the box in row-major order, 32 pixels per step; (xx, yy) advance incrementally (no division)
+            int xx = lane, yy = 0;
+            while (xx >= sbw) { xx -= sbw; yy++; }
             for (int k = lane; k < sarea; k += 32) {
-                const int yy = k / sbw, xx = k - yy * sbw;
                 test_pixel(s, sidx, s.xmin + xx, s.ymin + yy, h, w, keys);
+                xx += 32;
+                while (xx >= sbw) { xx -= sbw; yy++; }
             }
         }
     }
@@ -134,8 +138,11 @@ f3d_pass2_kernel(float* __restrict__ image, const float* __restrict__ vertices, 
                  const float* __restrict__ colors, float* __restrict__ depth, int nver, int ntri, int h, int w, int c,
                  const unsigned long long* __restrict__ keys)
 {
-    const long long npix = (long long)h * w;
-    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+    // one thread per pixel, rows from blockIdx.y (grid-strided): no integer division, coalesced key/depth/image rows
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        const size_t pix = (size_t)y * w + x;
         const unsigned long long key = keys[pix];
         if (key == 0ull) continue;
         const int idx = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
@@ -145,14 +152,22 @@ f3d_pass2_kernel(float* __restrict__ image, const float* __restrict__ vertices, 
         t.x0 = vertices[3 * i0]; t.y0 = vertices[3 * i0 + 1]; t.z0 = vertices[3 * i0 + 2];
         t.x1 = vertices[3 * i1]; t.y1 = vertices[3 * i1 + 1]; t.z1 = vertices[3 * i1 + 2];
         t.x2 = vertices[3 * i2]; t.y2 = vertices[3 * i2 + 1]; t.z2 = vertices[3 * i2 + 2];
-        const int y = (int)(pix / w), x = (int)(pix - (long long)y * w);
         float w0, w1, w2; bool inside;
         bary((float)x, (float)y, t, w0, w1, w2, inside);
         const float d = w0 * t.z0 + w1 * t.z1 + w2 * t.z2;
         if (!(d > depth[pix])) continue;
-        for (int k = 0; k < c; k++) {
-            const float c0 = colors[(size_t)c * i0 + k], c1 = colors[(size_t)c * i1 + k], c2 = colors[(size_t)c * i2 + k];
-            image[pix * c + k] = w0 * c0 + w1 * c1 + w2 * c2;
+        if (c == 3) {
+            const float* __restrict__ a0 = colors + 3 * (size_t)i0; const float* __restrict__ a1 = colors + 3 * (size_t)i1;
+            const float* __restrict__ a2 = colors + 3 * (size_t)i2;
+            float* __restrict__ o = image + pix * 3;
+            o[0] = w0 * a0[0] + w1 * a1[0] + w2 * a2[0];
+            o[1] = w0 * a0[1] + w1 * a1[1] + w2 * a2[1];
+            o[2] = w0 * a0[2] + w1 * a1[2] + w2 * a2[2];
+        } else {
+            for (int k = 0; k < c; k++) {
+                const float c0 = colors[(size_t)c * i0 + k], c1 = colors[(size_t)c * i1 + k], c2 = colors[(size_t)c * i2 + k];
+                image[pix * c + k] = w0 * c0 + w1 * c1 + w2 * c2;
+            }
         }
         depth[pix] = d;
     }
@@ -201,9 +216,8 @@ extern "C" int f3d_render_colors(float* image, const float* vertices, const int3
     long long blocks1 = (warps_needed + 7) / 8;
     if (blocks1 > (long long)sms * 64) blocks1 = (long long)sms * 64;
     f3d_pass1_kernel<<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, keys);
-    long long blocks2 = ((long long)h * w + 255) / 256;
-    if (blocks2 > (long long)sms * 32) blocks2 = (long long)sms * 32;
-    f3d_pass2_kernel<<<(unsigned)blocks2, 256, 0, s>>>(image, vertices, triangles, colors, depth_buffer, nver, ntri, h, w, c, keys);
+    const dim3 grid2((unsigned)((w + 255) / 256), (unsigned)(h < 65535 ? h : 65535));
+    f3d_pass2_kernel<<<grid2, 256, 0, s>>>(image, vertices, triangles, colors, depth_buffer, nver, ntri, h, w, c, keys);
     e = cudaGetLastError();
     return e == cudaSuccess ? F3D_OK : F3D_E_CUDA;
 }

@@ -36,7 +36,13 @@ namespace {
 // PX = 4 minimises instructions per (pixel, Gaussian) pair and is used when there are enough non-empty tiles
 // to fill the GPU; PX = 2 / 1 trade instructions for 2x / 4x more warps per tile when there are few tiles
 // (small scenes, one view per GPU): the per-tile latency, not the throughput, bounds those launches.
-constexpr int CHUNK = 64;                     // records per bulk copy (3 KB)
+#ifndef GS_CHUNK
+#define GS_CHUNK 64
+#endif
+#ifndef GS_BWD_MINB
+#define GS_BWD_MINB 1
+#endif
+constexpr int CHUNK = GS_CHUNK;               // records per bulk copy (64 -> 3 KB); must stay <= 64 (touched bitmask)
 #ifndef GS_FWD_UNROLL
 #define GS_FWD_UNROLL 2
 #endif
@@ -305,7 +311,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
 }
 
 template <int PX>
-__global__ void __launch_bounds__(256 / PX)
+__global__ void __launch_bounds__(256 / PX, PX == 4 ? GS_BWD_MINB : 1)
 blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
 {
     constexpr int BT = 256 / PX, NW = PX == 8 ? 1 : 8 / PX;
