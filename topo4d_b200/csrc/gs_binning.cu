@@ -220,7 +220,6 @@ __device__ __forceinline__ unsigned block_reach_mask(const float4 g0, const floa
     return mask;
 }
 
-template <bool WITH_MASK>
 __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParams p)
 {
     __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
@@ -262,9 +261,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParam
             const unsigned long long key = sorted[k];
             const uint32_t id = (uint32_t)key & 0x00ffffffu;
             p.sorted_ids[start + k] = id;
-            // only the PX = 1 / 2 blend variants read the mask (see gs_blend.cu); the other instantiation stays lean
-            unsigned mask = 0xffu;
-            if constexpr (WITH_MASK) mask = block_reach_mask(__ldg(geom + (size_t)id * 3), __ldg(geom + (size_t)id * 3 + 1), tx0, ty0);
+            const unsigned mask = block_reach_mask(__ldg(geom + (size_t)id * 3), __ldg(geom + (size_t)id * 3 + 1), tx0, ty0);
             sorted[k] = key | ((unsigned long long)mask << 24);
         }
         __syncthreads();
@@ -294,6 +291,5 @@ void gs_launch_sort_gather(const GsParams& p, int num_sms, cudaStream_t s)
     const long long maxb = (long long)num_sms * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    if (p.blend_px == 1 || p.blend_px == 2) sort_gather_kernel<true><<<(unsigned)blocks, SORT_THREADS, 0, s>>>(p);
-    else sort_gather_kernel<false><<<(unsigned)blocks, SORT_THREADS, 0, s>>>(p);
+    sort_gather_kernel<<<(unsigned)blocks, SORT_THREADS, 0, s>>>(p);
 }

@@ -5,42 +5,55 @@
 // Same per-pixel semantics (alpha = min(0.99, o*exp(power)), skip alpha < 1/255,
 // stop at T(1-alpha) < 1e-4, straight-through cap in backward); the machine mapping is new:
 //
-//   * work = (view, 16x16 binning tile).  Persistent 64-thread CTAs pull tiles from device-side queues
-//     (atomic counters in the status block): the compacted list of NON-EMPTY tiles, and -- forward only --
-//     groups of 16 tiles whose empty members just receive the background.  Even CTAs start on the heavy
-//     queue, odd CTAs on the fill queue, so the issue-bound blending and the HBM-bound background stream
-//     overlap on every SM and nobody idles on a static tile->CTA map.
-//   * a thread owns a vertical comb of 4 pixels (x, y+4k): lane (lx,ly) of warp w sits at column 8w+lx,
-//     rows ly+4k.  The column terms of the quadratic form are shared by the 4 pixels (3 FP ops per pixel
-//     for `power`), and pixel slot k of a warp is one COMPACT 8x4 block, so the divergent blend code of a
-//     slot runs only when the splat reaches that block and with a dense lane mask.
+//   * work = (view, 16x16 binning tile).  Persistent CTAs pull tiles from device-side queues (atomic counters in
+//     the status block): the compacted list of NON-EMPTY tiles, and -- forward only -- groups of 16 tiles whose
+//     empty members just receive the background.  Even CTAs start on the heavy queue, odd CTAs on the fill
+//     queue, so the issue-bound blending and the HBM-bound background stream overlap on every SM and nobody
+//     idles on a static tile->CTA map.
+//   * a thread owns a vertical comb of PX pixels (x, y+4k): lane (lx,ly) of a warp sits at column lx of the
+//     warp's 8 columns, rows ly+4k.  The column terms of the quadratic form are shared by the PX pixels (3 FP
+//     ops per pixel for `power`), and pixel slot k of a warp is one COMPACT 8x4 block, so the divergent blend
+//     code of a slot runs only when the splat reaches that block and with a dense lane mask.
+//   * warp-level compaction: every record carries the mask of the 8x4 blocks it can reach (gs_binning.cu); lane l
+//     tests record l of a 32-record group, a ballot yields the records that can touch THIS warp's blocks (about
+//     half of them at PX = 4) and only those are walked.
 //   * a conservative per-Gaussian threshold `thr` (stored in the record) rejects a pixel without touching
-//     exp(); ~88 % of (pixel, Gaussian) pairs leave after 5 instructions.
+//     exp(); ~88 % of (pixel, Gaussian) pairs leave after 3 instructions.  Finished / out-of-image pixels are
+//     parked at y = 1e18, which fails that same test, so the walk carries no per-pixel state checks.
 //   * the tile's depth-sorted 48-byte records are contiguous in HBM (gs_binning.cu): a chunk of 64
 //     records is ONE cp.async.bulk (SASS UBLKCP) into shared memory, double-buffered on two mbarriers.
 //   * backward replays back-to-front from the tile's deepest contributor with T_i = T_{i+1}/(1-alpha_i).
 //     alpha is re-derived by the SAME inlined code as in the forward (identical bits), so the division
 //     undoes the forward's multiplication to within ulps and nothing is amplified by 1/(1-alpha); the
-//     colour/depth/alpha "behind" terms are plain suffix sums built from the back (small terms first).
-//     The 10 per-Gaussian partials are pre-added over a thread's 4 pixels, reduced across the warp with a
-//     halving butterfly (16 shuffles instead of 50), parked in a per-warp shared-memory slot (no atomics)
-//     and flushed with three 16-byte vector REDs per (tile, Gaussian).
+//     colour/depth/alpha "behind" terms collapse into one scalar suffix sum per pixel (see Q below).
+//     Per (pixel, Gaussian) only the ten MOMENTS t, t dx, t dy, t dx^2, t dx dy, t dy^2, w g_* are accumulated
+//     (t = G dL/dalpha); they are pre-added over a thread's pixels, reduced across the warp through a
+//     shared-memory transpose, parked in a per-warp slot (no atomics), turned into the conic / position /
+//     opacity gradients ONCE per (tile, Gaussian) at flush time and added to HBM with three 16-byte vector REDs.
 #include "gs_common.cuh"
 
 namespace {
 
-// PX = pixels per thread (8, 4, 2 or 1).  A tile is always 256 pixels, so a CTA has 256/PX threads = 8/PX warps;
+// PX = pixels per thread (4, 2 or 1).  A tile is always 256 pixels, so a CTA has 256/PX threads = 8/PX warps;
 // warp w sits at columns 8*(w&1).. and rows (w>>1)*4*PX.., lane (lx,ly) owns pixels (8*(w&1)+lx, base+ly+4k).
-// PX = 8 is one warp per tile: lane (lx,ly) owns two columns (lx, lx+8) x four rows (ly+4k), slot k = column*4+row;
-// no __syncthreads between warps, one gradient reduction per (tile, Gaussian).
 // PX = 4 minimises instructions per (pixel, Gaussian) pair and is used when there are enough non-empty tiles
 // to fill the GPU; PX = 2 / 1 trade instructions for 2x / 4x more warps per tile when there are few tiles
 // (small scenes, one view per GPU): the per-tile latency, not the throughput, bounds those launches.
 #ifndef GS_CHUNK
 #define GS_CHUNK 64
 #endif
+// Minimum resident CTAs per SM asked of ptxas for the PX = 4 instantiations (64-thread CTAs): after the warp-level
+// compaction the record loop is a dependent ffs -> address -> LDS -> FMA chain, so the kernels want warps more than
+// registers (measured: bwd 12 -> 72 regs, fwd 14 -> 70 regs, no spills, 5-8 % faster than the unconstrained build).
 #ifndef GS_BWD_MINB
-#define GS_BWD_MINB 1
+#define GS_BWD_MINB 12
+#endif
+#ifndef GS_FWD_MINB
+#define GS_FWD_MINB 14
+#endif
+// 1 = load the next live record while the current one is blended; costs registers and lost (measured), kept for experiments
+#ifndef GS_PREFETCH
+#define GS_PREFETCH 0
 #endif
 constexpr int CHUNK = GS_CHUNK;               // records per bulk copy (64 -> 3 KB); must stay <= 64 (touched bitmask)
 #ifndef GS_FWD_UNROLL
@@ -92,6 +105,44 @@ __device__ __forceinline__ float splat_exp(float power)
 __device__ __forceinline__ float splat_alpha(float opacity, float G) { return fminf(GS_ALPHA_CAP, __fmul_rn(opacity, G)); }
 __device__ __forceinline__ float next_T(float T, float alpha) { return __fmul_rn(T, __fsub_rn(1.0f, alpha)); }
 
+// bits (within the record's 8-bit block-reach mask, bit b = 8x4 block row b>>1, column b&1) of the blocks warp `warp`
+// of a PX-pixels-per-thread CTA owns
+template <int PX>
+__device__ __forceinline__ unsigned warp_blocks(int warp)
+{
+    constexpr unsigned rows = PX == 4 ? 0x55u : (PX == 2 ? 0x5u : 0x1u);       // PX consecutive block rows of one column
+    return rows << (((warp >> 1) * PX) * 2 + (warp & 1));
+}
+
+// A pixel that takes no further part (finished, or outside the image) is parked here: its `power` against any
+// record is about -1e36 * conic.C, below every thr (gs_preprocess.cu clamps thr at -1e20), so the record walk
+// needs no per-pixel state test.
+constexpr float PARKED_Y = 1.0e18f;
+
+// 32-bit shared-memory addresses that the compiler must keep in a register instead of re-deriving them from
+// threadIdx.x inside the hot loop (it does, under the register cap: +15 integer instructions per reduction)
+__device__ __forceinline__ uint32_t pinned_smem_addr(const void* ptr)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(ptr);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float x)
+{
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(x) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+
 // ---- work queues ----
 constexpr long long ITEM_DONE = -1;
 // returns a global tile id (>= 0), a fill group encoded as -(g + 2), or ITEM_DONE
@@ -140,24 +191,18 @@ __device__ __forceinline__ void store4(float* __restrict__ plane, size_t pix0, f
 }
 
 template <int PX>
-__global__ void __launch_bounds__(256 / PX)
+__global__ void __launch_bounds__(256 / PX, PX == 4 ? GS_FWD_MINB : 1)
 blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restrict__ out_depth,
                  float* __restrict__ out_alpha)
 {
     constexpr int BT = 256 / PX;
-    constexpr int NC = PX == 8 ? 2 : 1, NR = PX / NC;        // columns x rows of a thread's pixel comb; slot k = col*NR + row
     __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cx = (PX == 8 ? 0 : (warp & 1) * 8) + (lane & 7), cy = (PX == 8 ? 0 : (warp >> 1) * (4 * PX)) + (lane >> 3);
+    const int cx = (warp & 1) * 8 + (lane & 7), cy = (warp >> 1) * (4 * PX) + (lane >> 3);
     constexpr unsigned ALL = (1u << PX) - 1u;
-    constexpr unsigned BLK_MASK = PX == 8 ? 0x5555u : (PX == 4 ? 0x55u : (PX == 2 ? 0x5u : 0x1u));   // slot k <-> bit 2k after the shift
-    // The per-instance block-reach mask pays off when a warp owns few 8x4 blocks (PX 1, 2); at PX = 4 a warp owns half
-    // the tile, the mask is rarely empty and its bookkeeping costs more than it saves (measured), so it is ignored
-    // there (and the gather kernel does not compute it).
-    constexpr bool USE_MASK = PX < 4;
-    const unsigned blk_shift = 24u + (unsigned)(((warp >> 1) * PX) * 2 + (warp & 1));
+    const unsigned my_blocks = warp_blocks<PX>(warp);
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t phases = 0u;                       // bit b = parity to wait for on s_bar[b]
@@ -199,17 +244,15 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
 
         // ---- one non-empty tile ----
         const TileCtx tc = tile_ctx(p, item);
-        float pxf[NC], pyf[NR], T[PX], C0[PX], C1[PX], C2[PX], D[PX], A[PX];
+        const float pxf = (float)(tc.tx0 + cx);
+        float pyf[PX], T[PX], C0[PX], C1[PX], C2[PX], D[PX], A[PX];
         uint32_t last[PX];
         unsigned done = 0;                                      // bit k: pixel k finished (or outside)
         #pragma unroll
-        for (int c2 = 0; c2 < NC; c2++) pxf[c2] = (float)(tc.tx0 + cx + 8 * c2);
-        #pragma unroll
-        for (int k4 = 0; k4 < NR; k4++) pyf[k4] = (float)(tc.ty0 + cy + 4 * k4);
-        #pragma unroll
         for (int k = 0; k < PX; k++) {
             T[k] = 1.f; C0[k] = C1[k] = C2[k] = D[k] = A[k] = 0.f; last[k] = 0u;
-            if (tc.tx0 + cx + 8 * (k / NR) >= p.W || tc.ty0 + cy + 4 * (k % NR) >= p.H) done |= 1u << k;
+            pyf[k] = (float)(tc.ty0 + cy + 4 * k);
+            if (tc.tx0 + cx >= p.W || tc.ty0 + cy + 4 * k >= p.H) { done |= 1u << k; pyf[k] = PARKED_Y; }
         }
         const unsigned outside = done;
         const int nchunks = (tc.n + CHUNK - 1) / CHUNK;
@@ -231,52 +274,49 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
             phases ^= 1u << cur;
             const int cnt = min(tc.n - c * CHUNK, CHUNK);
             const float4* __restrict__ rec = s_rec[cur];
-            // Structured per-record body (no break/continue out of divergent code) closed by __syncwarp(): the
+            const uint32_t* __restrict__ recw = reinterpret_cast<const uint32_t*>(s_rec[cur]);
+            // Warp-level compaction: lane l looks at the reach mask of record 32*half + l, a ballot turns the 32 answers
+            // into the list of records that can touch this warp's pixels at all (~half of them), and only those are
+            // walked.  Structured per-record body (no break/continue out of divergent code) closed by __syncwarp(): the
             // warp re-converges every record.  Leaving the loop from inside the divergent blend block makes the
             // compiler re-converge only at loop exit, which serialises the 32 lanes (measured: 12x slower).
-            if (!__all_sync(0xffffffffu, done == ALL)) {
-                #pragma unroll FWD_UNROLL
-                for (int j = 0; j < cnt; j++) {
-                    // bits of the 8x4 blocks this warp's pixel slots live in (set by the gather kernel); warp-uniform
-                    const unsigned bm = USE_MASK ? (__float_as_uint(rec[j * 3 + 2].w) >> blk_shift) & BLK_MASK : BLK_MASK;
-                    if (bm != 0u) {
-                        const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
-                        ColTerms ct[NC];
-                        float dyr[NR], pw[PX];
-                        #pragma unroll
-                        for (int c2 = 0; c2 < NC; c2++) ct[c2] = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf[c2]));
-                        #pragma unroll
-                        for (int k4 = 0; k4 < NR; k4++) dyr[k4] = __fsub_rn(r0.y, pyf[k4]);
-                        unsigned pass = 0;
+            #pragma unroll 1
+            for (int half = 0; half * 32 < cnt; half++) {
+                if (__all_sync(0xffffffffu, done == ALL)) break;
+                const int jl = half * 32 + lane;
+                unsigned live = __ballot_sync(0xffffffffu, jl < cnt && ((recw[jl * 12 + 11] >> 24) & my_blocks) != 0u);
+                while (live) {                                                  // warp-uniform
+                    const int j = half * 32 + __ffs(live) - 1;
+                    live &= live - 1u;
+                    const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
+                    const ColTerms ct = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf));
+                    float pw[PX];
+                    bool hit[PX], any = false;
+                    #pragma unroll
+                    for (int k = 0; k < PX; k++) {
+                        pw[k] = splat_power(ct, __fsub_rn(r0.y, pyf[k]));
+                        hit[k] = pw[k] >= r1.w;                                  // the (rare) power > 0 skip is tested on the blend path
+                        any = any || hit[k];
+                    }
+                    if (any) {
+                        const float4 r2 = rec[j * 3 + 2];
                         #pragma unroll
                         for (int k = 0; k < PX; k++) {
-                            pw[k] = 0.f;
-                            if (bm & (1u << (2 * k))) {
-                                pw[k] = splat_power(ct[k / NR], dyr[k % NR]);
-                                if (pw[k] >= r1.w) pass |= 1u << k;          // the (rare) power > 0 skip is tested on the blend path
-                            }
-                        }
-                        pass &= ~done;
-                        if (pass) {
-                            const float4 r2 = rec[j * 3 + 2];
-                            #pragma unroll
-                            for (int k = 0; k < PX; k++) {
-                                if (pass & (1u << k)) {
-                                    const float alpha = splat_alpha(r1.y, splat_exp(pw[k]));
-                                    const float test_T = next_T(T[k], alpha);
-                                    const bool visible = alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f;
-                                    const bool blend = visible && !(test_T < GS_T_MIN);
-                                    if (visible && !blend) done |= 1u << k;
-                                    if (blend) {
-                                        const float w = __fmul_rn(alpha, T[k]);
-                                        C0[k] = __fmaf_rn(r2.x, w, C0[k]);
-                                        C1[k] = __fmaf_rn(r2.y, w, C1[k]);
-                                        C2[k] = __fmaf_rn(r2.z, w, C2[k]);
-                                        D[k] = __fmaf_rn(r1.z, w, D[k]);
-                                        A[k] = __fadd_rn(A[k], w);
-                                        T[k] = test_T;
-                                        last[k] = (uint32_t)(c * CHUNK + j + 1);
-                                    }
+                            if (hit[k]) {
+                                const float alpha = splat_alpha(r1.y, splat_exp(pw[k]));
+                                const float test_T = next_T(T[k], alpha);
+                                const bool visible = alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f;
+                                const bool blend = visible && !(test_T < GS_T_MIN);
+                                if (visible && !blend) { done |= 1u << k; pyf[k] = PARKED_Y; }
+                                if (blend) {
+                                    const float w = __fmul_rn(alpha, T[k]);
+                                    C0[k] = __fmaf_rn(r2.x, w, C0[k]);
+                                    C1[k] = __fmaf_rn(r2.y, w, C1[k]);
+                                    C2[k] = __fmaf_rn(r2.z, w, C2[k]);
+                                    D[k] = __fmaf_rn(r1.z, w, D[k]);
+                                    A[k] = __fadd_rn(A[k], w);
+                                    T[k] = test_T;
+                                    last[k] = (uint32_t)(c * CHUNK + j + 1);
                                 }
                             }
                         }
@@ -297,7 +337,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
             #pragma unroll
             for (int k = 0; k < PX; k++) {
                 if (outside & (1u << k)) continue;
-                const size_t pix = (size_t)(tc.ty0 + cy + 4 * (k % NR)) * p.W + (tc.tx0 + cx + 8 * (k / NR));
+                const size_t pix = (size_t)(tc.ty0 + cy + 4 * k) * p.W + (tc.tx0 + cx);
                 p.final_T[vb + pix] = T[k];
                 p.n_contrib[vb + pix] = last[k];
                 out_color[vb * 3 + pix] = __fmaf_rn(T[k], b0, C0[k]);
@@ -314,8 +354,7 @@ template <int PX>
 __global__ void __launch_bounds__(256 / PX, PX == 4 ? GS_BWD_MINB : 1)
 blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
 {
-    constexpr int BT = 256 / PX, NW = PX == 8 ? 1 : 8 / PX;
-    constexpr int NC = PX == 8 ? 2 : 1, NR = PX / NC;
+    constexpr int BT = 256 / PX, NW = 8 / PX;
     __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
     __shared__ __align__(16) float s_acc[NW][CHUNK * GS_REC_FLOATS];    // one private slot array per warp
     __shared__ __align__(16) float s_tr[NW][32 * GS_REC_FLOATS];        // per-warp transpose scratch of the reduction
@@ -324,15 +363,18 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
     __shared__ uint32_t s_max[NW];
     __shared__ long long s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cx = (PX == 8 ? 0 : (warp & 1) * 8) + (lane & 7), cy = (PX == 8 ? 0 : (warp >> 1) * (4 * PX)) + (lane >> 3);
+    const int cx = (warp & 1) * 8 + (lane & 7), cy = (warp >> 1) * (4 * PX) + (lane >> 3);
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t phases = 0u;
     const size_t HW = (size_t)p.H * p.W;
-    constexpr unsigned BLK_MASK = PX == 8 ? 0x5555u : (PX == 4 ? 0x55u : (PX == 2 ? 0x5u : 0x1u));
-    constexpr bool USE_MASK = PX < 4;
-    const unsigned blk_shift = 24u + (unsigned)(((warp >> 1) * PX) * 2 + (warp & 1));
-    float* __restrict__ my_acc = s_acc[warp];
+    const unsigned my_blocks = warp_blocks<PX>(warp);
+    // reduction addresses (see below): where this lane parks its partial record, the column it sums, its result slot
+    const int red_c = lane & 15, red_h = lane >> 4;
+    const bool red_on = red_c < GS_REC_FLOATS;
+    const uint32_t a_park = pinned_smem_addr(&s_tr[warp][lane * GS_REC_FLOATS]);
+    const uint32_t a_col = pinned_smem_addr(&s_tr[warp][red_h * GS_REC_FLOATS + (red_on ? red_c : 0)]);
+    const uint32_t a_out = pinned_smem_addr(&s_acc[warp][red_on ? red_c : 0]);
 
     for (;;) {
         if (tid == 0) {
@@ -348,18 +390,16 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
         const float* __restrict__ bg = p.cams + (size_t)tc.v * GS_CAM_FLOATS + GS_CAM_BG;
         const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
 
-        // per-pixel state: T (recovered back-to-front), suffix sums B of what lies behind, loss gradients
+        // per-pixel state: T (recovered back-to-front), loss gradients g, and
         // Q[k] = g . (colour, depth, alpha accumulated BEHIND the current splat) + T_final (bg . g): because the loss
         // gradients g are per-pixel constants the five suffix sums collapse into this one scalar.
-        float pxf[NC], pyf[NR], T[PX], Q[PX], g0[PX], g1[PX], g2[PX], gd[PX], ga[PX];
+        const float pxf = (float)(tc.tx0 + cx);
+        float pyf[PX], T[PX], Q[PX], g0[PX], g1[PX], g2[PX], gd[PX], ga[PX];
         uint32_t last[PX];
         #pragma unroll
-        for (int c2 = 0; c2 < NC; c2++) pxf[c2] = (float)(tc.tx0 + cx + 8 * c2);
-        #pragma unroll
-        for (int k4 = 0; k4 < NR; k4++) pyf[k4] = (float)(tc.ty0 + cy + 4 * k4);
-        #pragma unroll
         for (int k = 0; k < PX; k++) {
-            const int px = tc.tx0 + cx + 8 * (k / NR), py = tc.ty0 + cy + 4 * (k % NR);
+            const int px = tc.tx0 + cx, py = tc.ty0 + cy + 4 * k;
+            pyf[k] = (float)py;
             T[k] = 0.f; last[k] = 0u; g0[k] = g1[k] = g2[k] = gd[k] = ga[k] = 0.f;
             if (px < p.W && py < p.H) {
                 const size_t pix = (size_t)py * p.W + px;
@@ -376,6 +416,7 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
         for (int k = 0; k < PX; k++) m = max(m, last[k]);
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const uint32_t wlast = m;                               // deepest contributor of this warp's pixels
         if (lane == 0) s_max[warp] = m;
         __syncthreads();
         uint32_t mm = 0u;
@@ -404,89 +445,98 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
             phases ^= 1u << cur;
             const int cnt = min(nmax - c * CHUNK, CHUNK);
             const float4* __restrict__ rec = s_rec[cur];
+            const uint32_t* __restrict__ recw = reinterpret_cast<const uint32_t*>(s_rec[cur]);
             unsigned long long touched = 0ull;                  // warp-uniform
-            for (int j = cnt - 1; j >= 0; j--) {
-                const uint32_t idx = (uint32_t)(c * CHUNK + j);
-                const unsigned bm = USE_MASK ? (__float_as_uint(rec[j * 3 + 2].w) >> blk_shift) & BLK_MASK : BLK_MASK;   // warp-uniform
-                if (USE_MASK && bm == 0u) continue;
-                const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
-                ColTerms ct[NC];
-                float dxc[NC], dyr[NR], pw[PX];
-                #pragma unroll
-                for (int c2 = 0; c2 < NC; c2++) { dxc[c2] = __fsub_rn(r0.x, pxf[c2]); ct[c2] = col_terms(r0.z, r0.w, r1.x, dxc[c2]); }
-                #pragma unroll
-                for (int k4 = 0; k4 < NR; k4++) dyr[k4] = __fsub_rn(r0.y, pyf[k4]);
-                unsigned pass = 0;
-                #pragma unroll
-                for (int k = 0; k < PX; k++) {
-                    pw[k] = 0.f;
-                    if (bm & (1u << (2 * k))) {
-                        pw[k] = splat_power(ct[k / NR], dyr[k % NR]);
-                        if (pw[k] >= r1.w && idx < last[k]) pass |= 1u << k;  // the (rare) power > 0 skip is tested on the blend path
-                    }
-                }
-                if (!__any_sync(0xffffffffu, pass != 0u)) continue;
-                float r[10];
-                #pragma unroll
-                for (int s = 0; s < 10; s++) r[s] = 0.f;
-                if (pass) {
-                    const float4 r2 = rec[j * 3 + 2];
+            // warp-level compaction (see the forward): only records whose reach mask meets this warp's 8x4 blocks and
+            // that lie in front of the warp's deepest contributor are walked, back to front
+            #pragma unroll 1
+            for (int half = (cnt - 1) >> 5; half >= 0; half--) {
+                const int jl = half * 32 + lane;
+                unsigned live = __ballot_sync(0xffffffffu, jl < cnt && (uint32_t)(c * CHUNK + jl) < wlast &&
+                                                               ((recw[jl * 12 + 11] >> 24) & my_blocks) != 0u);
+                while (live) {                                      // warp-uniform
+                    const int jb = 31 - __clz(live);
+                    live ^= 1u << jb;
+                    const int j = half * 32 + jb;
+                    const uint32_t idx = (uint32_t)(c * CHUNK + j);
+                    const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
+                    const float dx = __fsub_rn(r0.x, pxf);
+                    const ColTerms ct = col_terms(r0.z, r0.w, r1.x, dx);
+                    float dyr[PX], pw[PX];
+                    bool hit[PX], any = false;
                     #pragma unroll
                     for (int k = 0; k < PX; k++) {
-                        if (pass & (1u << k)) {
-                            const float G = splat_exp(pw[k]);
-                            const float alpha = splat_alpha(r1.y, G);
-                            if (alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f) {
-                                // the recovery T_i = T_{i+1} * (1/(1-alpha)) is replayed once per contributing layer (thousands
-                                // for very deep lists): a bare approximate reciprocal is biased and drifts past 1e-3, a
-                                // Newton-refined one does not (and __frcp_rn costs 15 % of the kernel)
-                                const float om = __fsub_rn(1.0f, alpha);             // in [0.01, 1]
-                                float ra;
-                                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(om));
-                                ra = __fmaf_rn(__fmaf_rn(-om, ra, 1.0f), ra, ra);    // one Newton step: <= 1 ulp, unbiased
-                                const float Tk = __fmul_rn(T[k], ra);            // undoes the forward's T*(1-alpha)
-                                const float w = __fmul_rn(alpha, Tk);
-                                // dL/dalpha_i = T_i (g . x_i) - (g . suffix_i + T_final bg.g) / (1 - alpha_i),  x_i = (rgb, depth, 1)
-                                const float Pk = __fmaf_rn(g0[k], r2.x, __fmaf_rn(g1[k], r2.y, __fmaf_rn(g2[k], r2.z, __fmaf_rn(gd[k], r1.z, ga[k]))));
-                                const float dLda = Tk * Pk - ra * Q[k];
-                                Q[k] = __fmaf_rn(w, Pk, Q[k]);
-                                const float sG = r1.y * dLda * G;                // dL/dG * G (straight-through the 0.99 cap)
-                                const float dx = dxc[k / NR], dy_ = dyr[k % NR];
-                                r[0] += sG * (-dx * r0.z - dy_ * r0.w);          // d/dpix.x
-                                r[1] += sG * (-dy_ * r1.x - dx * r0.w);          // d/dpix.y
-                                r[2] += -0.5f * sG * dx * dx;                    // d/dconA
-                                r[3] += -sG * dx * dy_;                          // d/dconB (true, not halved)
-                                r[4] += -0.5f * sG * dy_ * dy_;                  // d/dconC
-                                r[5] += G * dLda;                                // d/dopacity
-                                r[6] += w * gd[k];                               // d/ddepth
-                                r[7] += w * g0[k]; r[8] += w * g1[k]; r[9] += w * g2[k];
-                                T[k] = Tk;
+                        dyr[k] = __fsub_rn(r0.y, pyf[k]);
+                        pw[k] = splat_power(ct, dyr[k]);
+                        hit[k] = pw[k] >= r1.w && idx < last[k];       // the (rare) power > 0 skip is tested on the blend path
+                        any = any || hit[k];
+                    }
+                    if (!__any_sync(0xffffffffu, any)) continue;
+                    // moments of t = G dL/dalpha over this thread's pixels: {t dx, t dy, t dx^2, t dx dy | t dy^2, t, w g_d, - | w g_rgb}
+                    float r[10];
+                    #pragma unroll
+                    for (int s = 0; s < 10; s++) r[s] = 0.f;
+                    if (any) {
+                        const float4 r2 = rec[j * 3 + 2];
+                        #pragma unroll
+                        for (int k = 0; k < PX; k++) {
+                            if (hit[k]) {
+                                const float G = splat_exp(pw[k]);
+                                const float alpha = splat_alpha(r1.y, G);
+                                if (alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f) {
+                                    // the recovery T_i = T_{i+1} * (1/(1-alpha)) is replayed once per contributing layer (thousands
+                                    // for very deep lists): a bare approximate reciprocal is biased and drifts past 1e-3, a
+                                    // Newton-refined one does not (and __frcp_rn costs 15 % of the kernel)
+                                    const float om = __fsub_rn(1.0f, alpha);             // in [0.01, 1]
+                                    float ra;
+                                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(om));
+                                    ra = __fmaf_rn(__fmaf_rn(-om, ra, 1.0f), ra, ra);    // one Newton step: <= 1 ulp, unbiased
+                                    const float Tk = __fmul_rn(T[k], ra);            // undoes the forward's T*(1-alpha)
+                                    const float w = __fmul_rn(alpha, Tk);
+                                    // dL/dalpha_i = T_i (g . x_i) - (g . suffix_i + T_final bg.g) / (1 - alpha_i),  x_i = (rgb, depth, 1)
+                                    const float Pk = __fmaf_rn(g0[k], r2.x, __fmaf_rn(g1[k], r2.y, __fmaf_rn(g2[k], r2.z, __fmaf_rn(gd[k], r1.z, ga[k]))));
+                                    const float dLda = Tk * Pk - ra * Q[k];
+                                    Q[k] = __fmaf_rn(w, Pk, Q[k]);
+                                    // dL/dG * G = opacity * t (straight-through the 0.99 cap); the opacity, the conic entries and
+                                    // the -1/2 factors are constants of the record and are applied once, after the reduction
+                                    const float t = G * dLda;
+                                    const float tx = t * dx, ty = t * dyr[k];
+                                    r[0] += tx;
+                                    r[1] += ty;
+                                    r[2] = __fmaf_rn(tx, dx, r[2]);
+                                    r[3] = __fmaf_rn(tx, dyr[k], r[3]);
+                                    r[4] = __fmaf_rn(ty, dyr[k], r[4]);
+                                    r[5] += t;
+                                    r[6] = __fmaf_rn(w, gd[k], r[6]);
+                                    r[7] = __fmaf_rn(w, g0[k], r[7]); r[8] = __fmaf_rn(w, g1[k], r[8]); r[9] = __fmaf_rn(w, g2[k], r[9]);
+                                    T[k] = Tk;
+                                }
                             }
                         }
                     }
-                }
-                // warp reduction through shared memory: every lane parks its 12-float partial record (three 16-byte
-                // stores, conflict-free), then lane (c, h) = (lane & 15, lane >> 4) sums column c over rows 2i+h
-                // (16 conflict-free loads) and one shuffle joins the halves: ~40 instructions instead of a 16-shuffle /
-                // 32-select butterfly (~70).
-                {
-                    float4* tr = reinterpret_cast<float4*>(s_tr[warp]);
-                    tr[lane * 3 + 0] = make_float4(r[0], r[1], r[2], r[3]);
-                    tr[lane * 3 + 1] = make_float4(r[4], r[5], r[6], 0.f);
-                    tr[lane * 3 + 2] = make_float4(r[7], r[8], r[9], 0.f);
-                    __syncwarp();
-                    const int c = lane & 15, h = lane >> 4;
-                    float acc = 0.f;
-                    if (c < GS_REC_FLOATS) {
-                        const float* col = s_tr[warp] + h * GS_REC_FLOATS + c;
-                        #pragma unroll
-                        for (int i = 0; i < 16; i++) acc += col[i * 2 * GS_REC_FLOATS];
+                    // warp reduction through shared memory: every lane parks its 12-float partial record (three 16-byte
+                    // stores, conflict-free), then lane (c, h) = (lane & 15, lane >> 4) sums column c over rows 2i+h
+                    // (16 conflict-free loads) and one shuffle joins the halves: ~40 instructions instead of a 16-shuffle /
+                    // 32-select butterfly (~70).
+                    {
+                        sts_v4(a_park, r[0], r[1], r[2], r[3]);
+                        sts_v4(a_park + 16, r[4], r[5], r[6], 0.f);
+                        sts_v4(a_park + 32, r[7], r[8], r[9], 0.f);
+                        __syncwarp();
+                        float acc = 0.f;
+                        if (red_on) {
+                            constexpr int RS = 2 * GS_REC_FLOATS * 4;            // byte stride of two rows
+                            acc = ((lds_f32<0 * RS>(a_col) + lds_f32<1 * RS>(a_col)) + (lds_f32<2 * RS>(a_col) + lds_f32<3 * RS>(a_col))) +
+                                  ((lds_f32<4 * RS>(a_col) + lds_f32<5 * RS>(a_col)) + (lds_f32<6 * RS>(a_col) + lds_f32<7 * RS>(a_col)));
+                            acc += ((lds_f32<8 * RS>(a_col) + lds_f32<9 * RS>(a_col)) + (lds_f32<10 * RS>(a_col) + lds_f32<11 * RS>(a_col))) +
+                                   ((lds_f32<12 * RS>(a_col) + lds_f32<13 * RS>(a_col)) + (lds_f32<14 * RS>(a_col) + lds_f32<15 * RS>(a_col)));
+                        }
+                        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                        if (red_h == 0 && red_on) sts_f32(a_out + (uint32_t)j * (GS_REC_FLOATS * 4), acc);
+                        __syncwarp();
                     }
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-                    if (h == 0 && c < GS_REC_FLOATS) my_acc[j * GS_REC_FLOATS + c] = acc;
-                    __syncwarp();
+                    touched |= 1ull << j;
                 }
-                touched |= 1ull << j;
             }
             if (lane == 0) s_touched[warp] = touched;
             __syncthreads();
@@ -503,6 +553,12 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                     }
                 }
                 if (!any) continue;
+                // moments -> gradients of the 2-D record (pix.x, pix.y, conic A, B, C, opacity, depth, rgb); conic B is the
+                // true (not halved) derivative
+                const float4 q0 = rec[j * 3], q1 = rec[j * 3 + 1];
+                const float o = q1.y;
+                if (part == 0) a = make_float4(-o * (q0.z * a.x + q0.w * a.y), -o * (q1.x * a.y + q0.w * a.x), -0.5f * o * a.z, -o * a.w);
+                else if (part == 1) a.x = -0.5f * o * a.x;
                 const int id = __float_as_int(rec[j * 3 + 2].w) & 0x00ffffff;
                 red_add_v4(gbase + (size_t)id * 3 + part, a);
             }
@@ -521,7 +577,7 @@ int resident_ctas(const void* kernel, int block, int num_sms, int fallback_per_s
 }  // namespace
 
 // pixels per thread for this launch: the caller's hint, else 4 (throughput-optimal for many tiles)
-static int pick_px(const GsParams& p) { return (p.blend_px == 1 || p.blend_px == 2 || p.blend_px == 8) ? p.blend_px : 4; }
+static int pick_px(const GsParams& p) { return (p.blend_px == 1 || p.blend_px == 2) ? p.blend_px : 4; }
 
 template <int PX>
 static void launch_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s)
@@ -543,7 +599,6 @@ void gs_launch_blend_fwd(const GsParams& p, float* color, float* depth, float* a
     switch (pick_px(p)) {
         case 1: launch_fwd<1>(p, color, depth, alpha, num_sms, s); break;
         case 2: launch_fwd<2>(p, color, depth, alpha, num_sms, s); break;
-        case 8: launch_fwd<8>(p, color, depth, alpha, num_sms, s); break;
         default: launch_fwd<4>(p, color, depth, alpha, num_sms, s); break;
     }
 }
@@ -553,7 +608,6 @@ void gs_launch_blend_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms,
     switch (pick_px(p)) {
         case 1: launch_bwd<1>(p, io, num_sms, s); break;
         case 2: launch_bwd<2>(p, io, num_sms, s); break;
-        case 8: launch_bwd<8>(p, io, num_sms, s); break;
         default: launch_bwd<4>(p, io, num_sms, s); break;
     }
 }

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_kernel(const GsParams p, in
     // power >= -ln(255*opacity); the 1e-3 margin (0.1 % in alpha) dwarfs any fp32 rounding of power or exp,
     // so the prefilter can only pass extra pixels (which then fail the exact alpha test), never drop one.
     const float opac = p.opac[i];
-    const float thr = opac > 0.0f ? -logf(255.0f * opac) - 1.0e-3f : __int_as_float(0x7f800000);
+    const float thr = opac > 0.0f ? fmaxf(-logf(255.0f * opac) - 1.0e-3f, -1.0e20f) : __int_as_float(0x7f800000);   // >= -1e20: see PARKED_Y in gs_blend.cu
     g[1] = make_float4(cC, opac, tz, thr);
     g[2] = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(i));
 
