@@ -61,9 +61,10 @@ typedef struct GsProblem {
     int32_t sh_coeffs;              /* M: coefficients stored per Gaussian in `shs` [N,M,3]   */
     float   scale_modifier;
     int32_t debug;                  /* !=0: synchronise + check after every stage             */
-    int32_t blend_px;               /* tuning hint: pixels per thread in the blend kernels: 8 or 4 (many non-empty
+    int32_t blend_px;               /* tuning hint: pixels per thread in the blend kernels: 4 (many non-empty
                                        tiles: fewest instructions), 2 or 1 (few tiles: more warps per tile,
-                                       lower latency); 0 = library default (4).  Never changes results.   */
+                                       lower latency); 0 or any other value = library default (4).  Never
+                                       changes results.                                                   */
     int32_t reserved0;              /* must be 0 */
     int64_t cap_instances;          /* capacity (tile,Gaussian) instances of the workspace    */
     /* inputs, DEVICE pointers, fp32, contiguous.  Exactly one of shs|colors_precomp and

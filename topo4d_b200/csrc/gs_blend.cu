@@ -40,26 +40,24 @@ namespace {
 // to fill the GPU; PX = 2 / 1 trade instructions for 2x / 4x more warps per tile when there are few tiles
 // (small scenes, one view per GPU): the per-tile latency, not the throughput, bounds those launches.
 #ifndef GS_CHUNK
-#define GS_CHUNK 64
+#define GS_CHUNK 32
 #endif
-// Minimum resident CTAs per SM asked of ptxas for the PX = 4 instantiations (64-thread CTAs): after the warp-level
-// compaction the record loop is a dependent ffs -> address -> LDS -> FMA chain, so the kernels want warps more than
-// registers (measured: bwd 12 -> 72 regs, fwd 14 -> 70 regs, no spills, 5-8 % faster than the unconstrained build).
+constexpr int CHUNK = GS_CHUNK;               // records per bulk copy (32 -> 1.5 KB) = one ballot of the compaction
+static_assert(CHUNK == 32, "one 32-bit ballot per chunk");
+// Warps are independent workers (own work item, own record ring, own mbarriers); a CTA is just a container.
+#ifndef GS_WPC
+#define GS_WPC 4
+#endif
+constexpr int WPC = GS_WPC;
+// Minimum resident CTAs per SM asked of ptxas: after the warp-level compaction the record loop is a dependent
+// ffs -> address -> LDS -> FMA chain, so the kernels want warps more than registers (measured at 64-thread CTAs:
+// bwd 12 -> 72 regs, fwd 14 -> 70 regs, no spills, 5-8 % faster than the unconstrained build).
 #ifndef GS_BWD_MINB
-#define GS_BWD_MINB 12
+#define GS_BWD_MINB (24 / GS_WPC)
 #endif
 #ifndef GS_FWD_MINB
-#define GS_FWD_MINB 14
+#define GS_FWD_MINB (28 / GS_WPC)
 #endif
-// 1 = load the next live record while the current one is blended; costs registers and lost (measured), kept for experiments
-#ifndef GS_PREFETCH
-#define GS_PREFETCH 0
-#endif
-constexpr int CHUNK = GS_CHUNK;               // records per bulk copy (64 -> 3 KB); must stay <= 64 (touched bitmask)
-#ifndef GS_FWD_UNROLL
-#define GS_FWD_UNROLL 2
-#endif
-constexpr int FWD_UNROLL = GS_FWD_UNROLL;
 constexpr uint32_t REC_BYTES = 48;
 [[maybe_unused]] constexpr float LOG2E = 1.4426950408889634f;
 
@@ -144,8 +142,17 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 }
 
 // ---- work queues ----
+// A work item is one warp's share of a non-empty tile: sub-block `sub` of the 8 / PX a tile splits into (PX = 4: the
+// left / right 8 x 16 half).  Items are encoded tile * 8 + sub; a background-fill group as -(g + 2).
 constexpr long long ITEM_DONE = -1;
-// returns a global tile id (>= 0), a fill group encoded as -(g + 2), or ITEM_DONE
+template <int NWT>
+__device__ __forceinline__ long long fetch_heavy(const GsParams& p, unsigned int* cursor)
+{
+    const unsigned q = atomicAdd(cursor, 1u);
+    const long long t = gs_active_tile(p, q / NWT);
+    return t >= 0 ? t * 8 + (long long)(q % NWT) : ITEM_DONE;
+}
+template <int NWT>
 __device__ __forceinline__ long long fetch_fwd(const GsParams& p, bool prefer_fill, unsigned n_groups)
 {
     GsStatusDev* st = p.status;
@@ -156,8 +163,8 @@ __device__ __forceinline__ long long fetch_fwd(const GsParams& p, bool prefer_fi
             const unsigned g = atomicAdd(&st->q_fwd_fill, 1u);
             if (g < n_groups) return -((long long)g + 2);
         } else {
-            const long long t = gs_active_tile(p, atomicAdd(&st->q_fwd_heavy, 1u));
-            if (t >= 0) return t;
+            const long long it = fetch_heavy<NWT>(p, &st->q_fwd_heavy);
+            if (it >= 0) return it;
         }
     }
     return ITEM_DONE;
@@ -191,40 +198,38 @@ __device__ __forceinline__ void store4(float* __restrict__ plane, size_t pix0, f
 }
 
 template <int PX>
-__global__ void __launch_bounds__(256 / PX, PX == 4 ? GS_FWD_MINB : 1)
+__global__ void __launch_bounds__(WPC * 32, GS_FWD_MINB)
 blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restrict__ out_depth,
                  float* __restrict__ out_alpha)
 {
-    constexpr int BT = 256 / PX;
-    __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ long long s_item;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cx = (warp & 1) * 8 + (lane & 7), cy = (warp >> 1) * (4 * PX) + (lane >> 3);
+    constexpr int NWT = 8 / PX;                                 // warps (work items) per tile
+    __shared__ __align__(128) float4 s_rec[WPC][2][CHUNK * 3];
+    __shared__ __align__(8) uint64_t s_bar[WPC][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 (*const ring)[CHUNK * 3] = s_rec[warp];
+    uint64_t* const bar = s_bar[warp];
     constexpr unsigned ALL = (1u << PX) - 1u;
-    const unsigned my_blocks = warp_blocks<PX>(warp);
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
-    __syncthreads();
-    uint32_t phases = 0u;                       // bit b = parity to wait for on s_bar[b]
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    __syncwarp();
+    uint32_t phases = 0u;                       // bit b = parity to wait for on bar[b]
     const size_t HW = (size_t)p.H * p.W;
     const bool vec = (p.W & 3) == 0;
     const unsigned n_groups = (unsigned)((p.total_tiles + GS_FILL_GROUP - 1) / GS_FILL_GROUP);
-    const bool prefer_fill = blockIdx.x & 1;
+    const bool prefer_fill = (blockIdx.x * WPC + warp) & 1;
 
     for (;;) {
-        if (tid == 0) s_item = fetch_fwd(p, prefer_fill, n_groups);
-        __syncthreads();
-        const long long item = s_item;
-        __syncthreads();
+        long long item = 0;
+        if (lane == 0) item = fetch_fwd<NWT>(p, prefer_fill, n_groups);
+        item = __shfl_sync(0xffffffffu, item, 0);
         if (item == ITEM_DONE) break;
 
         if (item < 0) {
             // ---- background fill of the empty tiles of one group (work item = 4x1 pixel strip of one tile) ----
             const long long t0 = (-item - 2) * GS_FILL_GROUP;
-            for (int it = tid; it < GS_FILL_GROUP * 64; it += BT) {
+            for (int it = lane; it < GS_FILL_GROUP * 64; it += 32) {
                 const long long tg = t0 + (it >> 6);
                 if (tg >= p.total_tiles) break;
-                if (p.tile_start[tg + 1] != p.tile_start[tg]) continue;          // non-empty: a heavy item owns it
+                if (p.tile_start[tg + 1] != p.tile_start[tg]) continue;          // non-empty: heavy items own it
                 const TileCtx tc = tile_ctx(p, tg);
                 const int x0 = tc.tx0 + 4 * (it & 3), y = tc.ty0 + ((it & 63) >> 2);
                 const int valid = y < p.H ? min(4, p.W - x0) : 0;
@@ -239,11 +244,15 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
                 store4(p.final_T + vb, pix0, 1.f, valid, vec);
                 store4(reinterpret_cast<float*>(p.n_contrib) + vb, pix0, 0.f, valid, vec);   // bit pattern 0
             }
+            __syncwarp();
             continue;
         }
 
-        // ---- one non-empty tile ----
-        const TileCtx tc = tile_ctx(p, item);
+        // ---- this warp's share of one non-empty tile ----
+        const int sub = (int)(item & 7);
+        const TileCtx tc = tile_ctx(p, item >> 3);
+        const int cx = (sub & 1) * 8 + (lane & 7), cy = (sub >> 1) * (4 * PX) + (lane >> 3);
+        const unsigned my_blocks = warp_blocks<PX>(sub);
         const float pxf = (float)(tc.tx0 + cx);
         float pyf[PX], T[PX], C0[PX], C1[PX], C2[PX], D[PX], A[PX];
         uint32_t last[PX];
@@ -257,76 +266,71 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
         const unsigned outside = done;
         const int nchunks = (tc.n + CHUNK - 1) / CHUNK;
         const float4* __restrict__ src = p.sorted_rec + tc.start * 3;
-        if (tid == 0 && nchunks > 0) {
+        if (lane == 0 && nchunks > 0) {
             const uint32_t bytes = (uint32_t)min(tc.n, CHUNK) * REC_BYTES;
-            mbar_expect_tx(&s_bar[0], bytes);
-            bulk_g2s(s_rec[0], src, bytes, &s_bar[0]);
+            mbar_expect_tx(&bar[0], bytes);
+            bulk_g2s(ring[0], src, bytes, &bar[0]);
         }
         for (int c = 0; c < nchunks; c++) {
             const int cur = c & 1;
             const bool have_next = c + 1 < nchunks;
-            if (have_next && tid == 0) {
+            __syncwarp();                                       // every lane is done reading ring[cur ^ 1]
+            if (have_next && lane == 0) {
                 const uint32_t bytes = (uint32_t)min(tc.n - (c + 1) * CHUNK, CHUNK) * REC_BYTES;
-                mbar_expect_tx(&s_bar[cur ^ 1], bytes);
-                bulk_g2s(s_rec[cur ^ 1], src + (size_t)(c + 1) * CHUNK * 3, bytes, &s_bar[cur ^ 1]);
+                mbar_expect_tx(&bar[cur ^ 1], bytes);
+                bulk_g2s(ring[cur ^ 1], src + (size_t)(c + 1) * CHUNK * 3, bytes, &bar[cur ^ 1]);
             }
-            mbar_wait(&s_bar[cur], (phases >> cur) & 1u);
+            mbar_wait(&bar[cur], (phases >> cur) & 1u);
             phases ^= 1u << cur;
             const int cnt = min(tc.n - c * CHUNK, CHUNK);
-            const float4* __restrict__ rec = s_rec[cur];
-            const uint32_t* __restrict__ recw = reinterpret_cast<const uint32_t*>(s_rec[cur]);
-            // Warp-level compaction: lane l looks at the reach mask of record 32*half + l, a ballot turns the 32 answers
-            // into the list of records that can touch this warp's pixels at all (~half of them), and only those are
-            // walked.  Structured per-record body (no break/continue out of divergent code) closed by __syncwarp(): the
-            // warp re-converges every record.  Leaving the loop from inside the divergent blend block makes the
-            // compiler re-converge only at loop exit, which serialises the 32 lanes (measured: 12x slower).
-            #pragma unroll 1
-            for (int half = 0; half * 32 < cnt; half++) {
-                if (__all_sync(0xffffffffu, done == ALL)) break;
-                const int jl = half * 32 + lane;
-                unsigned live = __ballot_sync(0xffffffffu, jl < cnt && ((recw[jl * 12 + 11] >> 24) & my_blocks) != 0u);
-                while (live) {                                                  // warp-uniform
-                    const int j = half * 32 + __ffs(live) - 1;
-                    live &= live - 1u;
-                    const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
-                    const ColTerms ct = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf));
-                    float pw[PX];
-                    bool hit[PX], any = false;
+            const float4* __restrict__ rec = ring[cur];
+            const uint32_t* __restrict__ recw = reinterpret_cast<const uint32_t*>(ring[cur]);
+            // Warp-level compaction: lane l looks at the reach mask of record l, a ballot turns the 32 answers into the
+            // list of records that can touch this warp's pixels at all (~half of them), and only those are walked.
+            // Structured per-record body (no break/continue out of divergent code) closed by __syncwarp(): the warp
+            // re-converges every record.  Leaving the loop from inside the divergent blend block makes the compiler
+            // re-converge only at loop exit, which serialises the 32 lanes (measured: 12x slower).
+            unsigned live = __ballot_sync(0xffffffffu, lane < cnt && ((recw[lane * 12 + 11] >> 24) & my_blocks) != 0u);
+            while (live) {                                                      // warp-uniform
+                const int j = __ffs(live) - 1;
+                live &= live - 1u;
+                const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
+                const ColTerms ct = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf));
+                float pw[PX];
+                bool hit[PX], any = false;
+                #pragma unroll
+                for (int k = 0; k < PX; k++) {
+                    pw[k] = splat_power(ct, __fsub_rn(r0.y, pyf[k]));
+                    hit[k] = pw[k] >= r1.w;                                      // the (rare) power > 0 skip is tested on the blend path
+                    any = any || hit[k];
+                }
+                if (any) {
+                    const float4 r2 = rec[j * 3 + 2];
                     #pragma unroll
                     for (int k = 0; k < PX; k++) {
-                        pw[k] = splat_power(ct, __fsub_rn(r0.y, pyf[k]));
-                        hit[k] = pw[k] >= r1.w;                                  // the (rare) power > 0 skip is tested on the blend path
-                        any = any || hit[k];
-                    }
-                    if (any) {
-                        const float4 r2 = rec[j * 3 + 2];
-                        #pragma unroll
-                        for (int k = 0; k < PX; k++) {
-                            if (hit[k]) {
-                                const float alpha = splat_alpha(r1.y, splat_exp(pw[k]));
-                                const float test_T = next_T(T[k], alpha);
-                                const bool visible = alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f;
-                                const bool blend = visible && !(test_T < GS_T_MIN);
-                                if (visible && !blend) { done |= 1u << k; pyf[k] = PARKED_Y; }
-                                if (blend) {
-                                    const float w = __fmul_rn(alpha, T[k]);
-                                    C0[k] = __fmaf_rn(r2.x, w, C0[k]);
-                                    C1[k] = __fmaf_rn(r2.y, w, C1[k]);
-                                    C2[k] = __fmaf_rn(r2.z, w, C2[k]);
-                                    D[k] = __fmaf_rn(r1.z, w, D[k]);
-                                    A[k] = __fadd_rn(A[k], w);
-                                    T[k] = test_T;
-                                    last[k] = (uint32_t)(c * CHUNK + j + 1);
-                                }
+                        if (hit[k]) {
+                            const float alpha = splat_alpha(r1.y, splat_exp(pw[k]));
+                            const float test_T = next_T(T[k], alpha);
+                            const bool visible = alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f;
+                            const bool blend = visible && !(test_T < GS_T_MIN);
+                            if (visible && !blend) { done |= 1u << k; pyf[k] = PARKED_Y; }
+                            if (blend) {
+                                const float w = __fmul_rn(alpha, T[k]);
+                                C0[k] = __fmaf_rn(r2.x, w, C0[k]);
+                                C1[k] = __fmaf_rn(r2.y, w, C1[k]);
+                                C2[k] = __fmaf_rn(r2.z, w, C2[k]);
+                                D[k] = __fmaf_rn(r1.z, w, D[k]);
+                                A[k] = __fadd_rn(A[k], w);
+                                T[k] = test_T;
+                                last[k] = (uint32_t)(c * CHUNK + j + 1);
                             }
                         }
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
-            const int all_done = __syncthreads_and(done == ALL);
-            if (all_done) {
-                if (have_next) { mbar_wait(&s_bar[cur ^ 1], (phases >> (cur ^ 1)) & 1u); phases ^= 1u << (cur ^ 1); }   // drain prefetch
+            if (__all_sync(0xffffffffu, done == ALL)) {
+                if (have_next) { mbar_wait(&bar[cur ^ 1], (phases >> (cur ^ 1)) & 1u); phases ^= 1u << (cur ^ 1); }   // drain prefetch
                 break;
             }
         }
@@ -347,45 +351,44 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
                 out_alpha[vb + pix] = A[k];
             }
         }
+        __syncwarp();
     }
 }
 
 template <int PX>
-__global__ void __launch_bounds__(256 / PX, PX == 4 ? GS_BWD_MINB : 1)
+__global__ void __launch_bounds__(WPC * 32, GS_BWD_MINB)
 blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
 {
-    constexpr int BT = 256 / PX, NW = 8 / PX;
-    __shared__ __align__(128) float4 s_rec[2][CHUNK * 3];
-    __shared__ __align__(16) float s_acc[NW][CHUNK * GS_REC_FLOATS];    // one private slot array per warp
-    __shared__ __align__(16) float s_tr[NW][32 * GS_REC_FLOATS];        // per-warp transpose scratch of the reduction
-    __shared__ unsigned long long s_touched[NW];                        // bit j: warp w wrote s_acc[w][j]
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_max[NW];
-    __shared__ long long s_item;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cx = (warp & 1) * 8 + (lane & 7), cy = (warp >> 1) * (4 * PX) + (lane >> 3);
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
-    __syncthreads();
+    constexpr int NWT = 8 / PX;
+    __shared__ __align__(128) float4 s_rec[WPC][2][CHUNK * 3];
+    __shared__ __align__(16) float s_acc[WPC][CHUNK * GS_REC_FLOATS];   // reduced moments of the chunk's records
+    __shared__ __align__(16) float s_tr[WPC][32 * GS_REC_FLOATS];       // transpose scratch of the reduction
+    __shared__ __align__(8) uint64_t s_bar[WPC][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 (*const ring)[CHUNK * 3] = s_rec[warp];
+    uint64_t* const bar = s_bar[warp];
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    __syncwarp();
     uint32_t phases = 0u;
     const size_t HW = (size_t)p.H * p.W;
-    const unsigned my_blocks = warp_blocks<PX>(warp);
     // reduction addresses (see below): where this lane parks its partial record, the column it sums, its result slot
     const int red_c = lane & 15, red_h = lane >> 4;
     const bool red_on = red_c < GS_REC_FLOATS;
     const uint32_t a_park = pinned_smem_addr(&s_tr[warp][lane * GS_REC_FLOATS]);
     const uint32_t a_col = pinned_smem_addr(&s_tr[warp][red_h * GS_REC_FLOATS + (red_on ? red_c : 0)]);
     const uint32_t a_out = pinned_smem_addr(&s_acc[warp][red_on ? red_c : 0]);
+    const float4* __restrict__ my_acc = reinterpret_cast<const float4*>(s_acc[warp]);
 
     for (;;) {
-        if (tid == 0) {
-            s_item = gs_active_tile(p, atomicAdd(&p.status->q_bwd_heavy, 1u));      // -1 == ITEM_DONE
-        }
-        __syncthreads();
-        const long long item = s_item;
-        __syncthreads();
+        long long item = 0;
+        if (lane == 0) item = fetch_heavy<NWT>(p, &p.status->q_bwd_heavy);
+        item = __shfl_sync(0xffffffffu, item, 0);
         if (item == ITEM_DONE) break;
 
-        const TileCtx tc = tile_ctx(p, item);
+        const int sub = (int)(item & 7);
+        const TileCtx tc = tile_ctx(p, item >> 3);
+        const int cx = (sub & 1) * 8 + (lane & 7), cy = (sub >> 1) * (4 * PX) + (lane >> 3);
+        const unsigned my_blocks = warp_blocks<PX>(sub);
         const size_t vb = (size_t)tc.v * HW;
         const float* __restrict__ bg = p.cams + (size_t)tc.v * GS_CAM_FLOATS + GS_CAM_BG;
         const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
@@ -416,145 +419,124 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
         for (int k = 0; k < PX; k++) m = max(m, last[k]);
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const uint32_t wlast = m;                               // deepest contributor of this warp's pixels
-        if (lane == 0) s_max[warp] = m;
-        __syncthreads();
-        uint32_t mm = 0u;
-        #pragma unroll
-        for (int w = 0; w < NW; w++) mm = max(mm, s_max[w]);
-        const int nmax = (int)min(mm, (uint32_t)tc.n);
-        if (nmax == 0) continue;                                // uniform; the next __syncthreads is after the fetch
+        const int nmax = (int)min(m, (uint32_t)tc.n);           // deepest contributor of this warp's pixels
+        if (nmax == 0) continue;                                // warp-uniform
 
         const int nchunks = (nmax + CHUNK - 1) / CHUNK;
         const float4* __restrict__ src = p.sorted_rec + tc.start * 3;
         float4* __restrict__ gbase = p.grad2d + (size_t)tc.v * p.N * 3;
-        if (tid == 0) {
+        if (lane == 0) {
             const int c = nchunks - 1;
             const uint32_t bytes = (uint32_t)(nmax - c * CHUNK) * REC_BYTES;
-            mbar_expect_tx(&s_bar[0], bytes);
-            bulk_g2s(s_rec[0], src + (size_t)c * CHUNK * 3, bytes, &s_bar[0]);
+            mbar_expect_tx(&bar[0], bytes);
+            bulk_g2s(ring[0], src + (size_t)c * CHUNK * 3, bytes, &bar[0]);
         }
         for (int kc = 0; kc < nchunks; kc++) {
             const int c = nchunks - 1 - kc, cur = kc & 1;
-            if (c > 0 && tid == 0) {
+            __syncwarp();                                       // every lane is done with ring[cur ^ 1] (walk and flush)
+            if (c > 0 && lane == 0) {
                 const uint32_t bytes = (uint32_t)CHUNK * REC_BYTES;              // every earlier chunk is full
-                mbar_expect_tx(&s_bar[cur ^ 1], bytes);
-                bulk_g2s(s_rec[cur ^ 1], src + (size_t)(c - 1) * CHUNK * 3, bytes, &s_bar[cur ^ 1]);
+                mbar_expect_tx(&bar[cur ^ 1], bytes);
+                bulk_g2s(ring[cur ^ 1], src + (size_t)(c - 1) * CHUNK * 3, bytes, &bar[cur ^ 1]);
             }
-            mbar_wait(&s_bar[cur], (phases >> cur) & 1u);
+            mbar_wait(&bar[cur], (phases >> cur) & 1u);
             phases ^= 1u << cur;
             const int cnt = min(nmax - c * CHUNK, CHUNK);
-            const float4* __restrict__ rec = s_rec[cur];
-            const uint32_t* __restrict__ recw = reinterpret_cast<const uint32_t*>(s_rec[cur]);
-            unsigned long long touched = 0ull;                  // warp-uniform
-            // warp-level compaction (see the forward): only records whose reach mask meets this warp's 8x4 blocks and
-            // that lie in front of the warp's deepest contributor are walked, back to front
-            #pragma unroll 1
-            for (int half = (cnt - 1) >> 5; half >= 0; half--) {
-                const int jl = half * 32 + lane;
-                unsigned live = __ballot_sync(0xffffffffu, jl < cnt && (uint32_t)(c * CHUNK + jl) < wlast &&
-                                                               ((recw[jl * 12 + 11] >> 24) & my_blocks) != 0u);
-                while (live) {                                      // warp-uniform
-                    const int jb = 31 - __clz(live);
-                    live ^= 1u << jb;
-                    const int j = half * 32 + jb;
-                    const uint32_t idx = (uint32_t)(c * CHUNK + j);
-                    const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
-                    const float dx = __fsub_rn(r0.x, pxf);
-                    const ColTerms ct = col_terms(r0.z, r0.w, r1.x, dx);
-                    float dyr[PX], pw[PX];
-                    bool hit[PX], any = false;
+            const float4* __restrict__ rec = ring[cur];
+            const uint32_t* __restrict__ recw = reinterpret_cast<const uint32_t*>(ring[cur]);
+            // warp-level compaction (see the forward): only records whose reach mask meets this warp's 8x4 blocks are
+            // walked, back to front
+            unsigned live = __ballot_sync(0xffffffffu, lane < cnt && ((recw[lane * 12 + 11] >> 24) & my_blocks) != 0u);
+            unsigned touched = 0u;                              // warp-uniform: records whose moments sit in s_acc
+            while (live) {                                      // warp-uniform
+                const int j = 31 - __clz(live);
+                live ^= 1u << j;
+                const uint32_t idx = (uint32_t)(c * CHUNK + j);
+                const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
+                const float dx = __fsub_rn(r0.x, pxf);
+                const ColTerms ct = col_terms(r0.z, r0.w, r1.x, dx);
+                float dyr[PX], pw[PX];
+                bool hit[PX], any = false;
+                #pragma unroll
+                for (int k = 0; k < PX; k++) {
+                    dyr[k] = __fsub_rn(r0.y, pyf[k]);
+                    pw[k] = splat_power(ct, dyr[k]);
+                    hit[k] = pw[k] >= r1.w && idx < last[k];           // the (rare) power > 0 skip is tested on the blend path
+                    any = any || hit[k];
+                }
+                if (!__any_sync(0xffffffffu, any)) continue;
+                // moments of t = G dL/dalpha over this thread's pixels: {t dx, t dy, t dx^2, t dx dy | t dy^2, t, w g_d, - | w g_rgb}
+                float r[10];
+                #pragma unroll
+                for (int s = 0; s < 10; s++) r[s] = 0.f;
+                if (any) {
+                    const float4 r2 = rec[j * 3 + 2];
                     #pragma unroll
                     for (int k = 0; k < PX; k++) {
-                        dyr[k] = __fsub_rn(r0.y, pyf[k]);
-                        pw[k] = splat_power(ct, dyr[k]);
-                        hit[k] = pw[k] >= r1.w && idx < last[k];       // the (rare) power > 0 skip is tested on the blend path
-                        any = any || hit[k];
-                    }
-                    if (!__any_sync(0xffffffffu, any)) continue;
-                    // moments of t = G dL/dalpha over this thread's pixels: {t dx, t dy, t dx^2, t dx dy | t dy^2, t, w g_d, - | w g_rgb}
-                    float r[10];
-                    #pragma unroll
-                    for (int s = 0; s < 10; s++) r[s] = 0.f;
-                    if (any) {
-                        const float4 r2 = rec[j * 3 + 2];
-                        #pragma unroll
-                        for (int k = 0; k < PX; k++) {
-                            if (hit[k]) {
-                                const float G = splat_exp(pw[k]);
-                                const float alpha = splat_alpha(r1.y, G);
-                                if (alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f) {
-                                    // the recovery T_i = T_{i+1} * (1/(1-alpha)) is replayed once per contributing layer (thousands
-                                    // for very deep lists): a bare approximate reciprocal is biased and drifts past 1e-3, a
-                                    // Newton-refined one does not (and __frcp_rn costs 15 % of the kernel)
-                                    const float om = __fsub_rn(1.0f, alpha);             // in [0.01, 1]
-                                    float ra;
-                                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(om));
-                                    ra = __fmaf_rn(__fmaf_rn(-om, ra, 1.0f), ra, ra);    // one Newton step: <= 1 ulp, unbiased
-                                    const float Tk = __fmul_rn(T[k], ra);            // undoes the forward's T*(1-alpha)
-                                    const float w = __fmul_rn(alpha, Tk);
-                                    // dL/dalpha_i = T_i (g . x_i) - (g . suffix_i + T_final bg.g) / (1 - alpha_i),  x_i = (rgb, depth, 1)
-                                    const float Pk = __fmaf_rn(g0[k], r2.x, __fmaf_rn(g1[k], r2.y, __fmaf_rn(g2[k], r2.z, __fmaf_rn(gd[k], r1.z, ga[k]))));
-                                    const float dLda = Tk * Pk - ra * Q[k];
-                                    Q[k] = __fmaf_rn(w, Pk, Q[k]);
-                                    // dL/dG * G = opacity * t (straight-through the 0.99 cap); the opacity, the conic entries and
-                                    // the -1/2 factors are constants of the record and are applied once, after the reduction
-                                    const float t = G * dLda;
-                                    const float tx = t * dx, ty = t * dyr[k];
-                                    r[0] += tx;
-                                    r[1] += ty;
-                                    r[2] = __fmaf_rn(tx, dx, r[2]);
-                                    r[3] = __fmaf_rn(tx, dyr[k], r[3]);
-                                    r[4] = __fmaf_rn(ty, dyr[k], r[4]);
-                                    r[5] += t;
-                                    r[6] = __fmaf_rn(w, gd[k], r[6]);
-                                    r[7] = __fmaf_rn(w, g0[k], r[7]); r[8] = __fmaf_rn(w, g1[k], r[8]); r[9] = __fmaf_rn(w, g2[k], r[9]);
-                                    T[k] = Tk;
-                                }
+                        if (hit[k]) {
+                            const float G = splat_exp(pw[k]);
+                            const float alpha = splat_alpha(r1.y, G);
+                            if (alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f) {
+                                // the recovery T_i = T_{i+1} * (1/(1-alpha)) is replayed once per contributing layer (thousands
+                                // for very deep lists): a bare approximate reciprocal is biased and drifts past 1e-3, a
+                                // Newton-refined one does not (and __frcp_rn costs 15 % of the kernel)
+                                const float om = __fsub_rn(1.0f, alpha);             // in [0.01, 1]
+                                float ra;
+                                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(om));
+                                ra = __fmaf_rn(__fmaf_rn(-om, ra, 1.0f), ra, ra);    // one Newton step: <= 1 ulp, unbiased
+                                const float Tk = __fmul_rn(T[k], ra);            // undoes the forward's T*(1-alpha)
+                                const float w = __fmul_rn(alpha, Tk);
+                                // dL/dalpha_i = T_i (g . x_i) - (g . suffix_i + T_final bg.g) / (1 - alpha_i),  x_i = (rgb, depth, 1)
+                                const float Pk = __fmaf_rn(g0[k], r2.x, __fmaf_rn(g1[k], r2.y, __fmaf_rn(g2[k], r2.z, __fmaf_rn(gd[k], r1.z, ga[k]))));
+                                const float dLda = Tk * Pk - ra * Q[k];
+                                Q[k] = __fmaf_rn(w, Pk, Q[k]);
+                                // dL/dG * G = opacity * t (straight-through the 0.99 cap); the opacity, the conic entries and
+                                // the -1/2 factors are constants of the record and are applied once, after the reduction
+                                const float t = G * dLda;
+                                const float tx = t * dx, ty = t * dyr[k];
+                                r[0] += tx;
+                                r[1] += ty;
+                                r[2] = __fmaf_rn(tx, dx, r[2]);
+                                r[3] = __fmaf_rn(tx, dyr[k], r[3]);
+                                r[4] = __fmaf_rn(ty, dyr[k], r[4]);
+                                r[5] += t;
+                                r[6] = __fmaf_rn(w, gd[k], r[6]);
+                                r[7] = __fmaf_rn(w, g0[k], r[7]); r[8] = __fmaf_rn(w, g1[k], r[8]); r[9] = __fmaf_rn(w, g2[k], r[9]);
+                                T[k] = Tk;
                             }
                         }
                     }
-                    // warp reduction through shared memory: every lane parks its 12-float partial record (three 16-byte
-                    // stores, conflict-free), then lane (c, h) = (lane & 15, lane >> 4) sums column c over rows 2i+h
-                    // (16 conflict-free loads) and one shuffle joins the halves: ~40 instructions instead of a 16-shuffle /
-                    // 32-select butterfly (~70).
-                    {
-                        sts_v4(a_park, r[0], r[1], r[2], r[3]);
-                        sts_v4(a_park + 16, r[4], r[5], r[6], 0.f);
-                        sts_v4(a_park + 32, r[7], r[8], r[9], 0.f);
-                        __syncwarp();
-                        float acc = 0.f;
-                        if (red_on) {
-                            constexpr int RS = 2 * GS_REC_FLOATS * 4;            // byte stride of two rows
-                            acc = ((lds_f32<0 * RS>(a_col) + lds_f32<1 * RS>(a_col)) + (lds_f32<2 * RS>(a_col) + lds_f32<3 * RS>(a_col))) +
-                                  ((lds_f32<4 * RS>(a_col) + lds_f32<5 * RS>(a_col)) + (lds_f32<6 * RS>(a_col) + lds_f32<7 * RS>(a_col)));
-                            acc += ((lds_f32<8 * RS>(a_col) + lds_f32<9 * RS>(a_col)) + (lds_f32<10 * RS>(a_col) + lds_f32<11 * RS>(a_col))) +
-                                   ((lds_f32<12 * RS>(a_col) + lds_f32<13 * RS>(a_col)) + (lds_f32<14 * RS>(a_col) + lds_f32<15 * RS>(a_col)));
-                        }
-                        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-                        if (red_h == 0 && red_on) sts_f32(a_out + (uint32_t)j * (GS_REC_FLOATS * 4), acc);
-                        __syncwarp();
-                    }
-                    touched |= 1ull << j;
                 }
+                // warp reduction through shared memory: every lane parks its 12-float partial record (three 16-byte
+                // stores, conflict-free), then lane (c, h) = (lane & 15, lane >> 4) sums column c over rows 2i+h
+                // (16 conflict-free loads) and one shuffle joins the halves: ~40 instructions instead of a 16-shuffle /
+                // 32-select butterfly (~70).
+                {
+                    sts_v4(a_park, r[0], r[1], r[2], r[3]);
+                    sts_v4(a_park + 16, r[4], r[5], r[6], 0.f);
+                    sts_v4(a_park + 32, r[7], r[8], r[9], 0.f);
+                    __syncwarp();
+                    float acc = 0.f;
+                    if (red_on) {
+                        constexpr int RS = 2 * GS_REC_FLOATS * 4;            // byte stride of two rows
+                        acc = ((lds_f32<0 * RS>(a_col) + lds_f32<1 * RS>(a_col)) + (lds_f32<2 * RS>(a_col) + lds_f32<3 * RS>(a_col))) +
+                              ((lds_f32<4 * RS>(a_col) + lds_f32<5 * RS>(a_col)) + (lds_f32<6 * RS>(a_col) + lds_f32<7 * RS>(a_col)));
+                        acc += ((lds_f32<8 * RS>(a_col) + lds_f32<9 * RS>(a_col)) + (lds_f32<10 * RS>(a_col) + lds_f32<11 * RS>(a_col))) +
+                               ((lds_f32<12 * RS>(a_col) + lds_f32<13 * RS>(a_col)) + (lds_f32<14 * RS>(a_col) + lds_f32<15 * RS>(a_col)));
+                    }
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                    if (red_h == 0 && red_on) sts_f32(a_out + (uint32_t)j * (GS_REC_FLOATS * 4), acc);
+                    __syncwarp();
+                }
+                touched |= 1u << j;
             }
-            if (lane == 0) s_touched[warp] = touched;
-            __syncthreads();
-            for (int t = tid; t < cnt * 3; t += BT) {
+            // flush the chunk: moments -> gradients of the 2-D record (pix.x, pix.y, conic A, B, C, opacity, depth, rgb),
+            // conic B being the true (not halved) derivative; one 16-byte vector RED per touched (record, part)
+            __syncwarp();
+            for (int t = lane; t < cnt * 3; t += 32) {
                 const int j = t / 3, part = t - j * 3;
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool any = false;
-                #pragma unroll
-                for (int w = 0; w < NW; w++) {
-                    if ((s_touched[w] >> j) & 1ull) {
-                        const float4 b = reinterpret_cast<const float4*>(s_acc[w])[t];
-                        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-                        any = true;
-                    }
-                }
-                if (!any) continue;
-                // moments -> gradients of the 2-D record (pix.x, pix.y, conic A, B, C, opacity, depth, rgb); conic B is the
-                // true (not halved) derivative
+                if (!((touched >> j) & 1u)) continue;
+                float4 a = my_acc[t];
                 const float4 q0 = rec[j * 3], q1 = rec[j * 3 + 1];
                 const float o = q1.y;
                 if (part == 0) a = make_float4(-o * (q0.z * a.x + q0.w * a.y), -o * (q1.x * a.y + q0.w * a.x), -0.5f * o * a.z, -o * a.w);
@@ -562,8 +544,8 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                 const int id = __float_as_int(rec[j * 3 + 2].w) & 0x00ffffff;
                 red_add_v4(gbase + (size_t)id * 3 + part, a);
             }
-            __syncthreads();
         }
+        __syncwarp();
     }
 }
 
@@ -583,15 +565,15 @@ template <int PX>
 static void launch_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s)
 {
     static thread_local int grid = 0, grid_sms = 0;
-    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_fwd_kernel<PX>, 256 / PX, num_sms, 4 * PX); grid_sms = num_sms; }
-    blend_fwd_kernel<PX><<<grid, 256 / PX, 0, s>>>(p, color, depth, alpha);
+    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_fwd_kernel<PX>, WPC * 32, num_sms, 4); grid_sms = num_sms; }
+    blend_fwd_kernel<PX><<<grid, WPC * 32, 0, s>>>(p, color, depth, alpha);
 }
 template <int PX>
 static void launch_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms, cudaStream_t s)
 {
     static thread_local int grid = 0, grid_sms = 0;
-    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_bwd_kernel<PX>, 256 / PX, num_sms, 2 * PX); grid_sms = num_sms; }
-    blend_bwd_kernel<PX><<<grid, 256 / PX, 0, s>>>(p, io);
+    if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_bwd_kernel<PX>, WPC * 32, num_sms, 4); grid_sms = num_sms; }
+    blend_bwd_kernel<PX><<<grid, WPC * 32, 0, s>>>(p, io);
 }
 
 void gs_launch_blend_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s)

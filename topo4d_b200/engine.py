@@ -43,9 +43,9 @@ def _pinned_slot() -> torch.Tensor:
 def pick_blend_px(num_active_tiles: int | None) -> int:
     """4 pixels/thread when there are enough non-empty tiles to fill the GPU (fewest instructions), 2 or 1 when
     there are few (more warps per tile: the per-tile latency bounds such launches).  Never changes results."""
-    if num_active_tiles is None or num_active_tiles >= 4096:
+    if num_active_tiles is None or num_active_tiles >= 20000:
         return 4
-    return 2 if num_active_tiles >= 1800 else 1
+    return 2 if num_active_tiles >= 3000 else 1
 
 
 def _ptr(t: torch.Tensor | None):
