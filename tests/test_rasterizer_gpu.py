@@ -159,11 +159,12 @@ def test_blend_px_variants_agree():
     assert engine.pick_blend_px(None) == 4 and engine.pick_blend_px(40000) == 4 and engine.pick_blend_px(5000) == 2 and engine.pick_blend_px(300) == 1
 
 
-def test_very_long_tile_lists_use_the_global_sort_path():
-    """Every tile list longer than the 4096-key shared-memory sort: in-place global bitonic sort, dozens of 64-record
-    chunks per tile, early termination deep inside the list."""
+@pytest.mark.parametrize("n", [5200, 1500, 700, 300])
+def test_very_long_tile_lists_use_the_global_sort_path(n):
+    """Every tile list has exactly n entries: n = 5200 is longer than the 2048-key register sort (in-place global bitonic
+    sort, dozens of record chunks per tile, early termination deep inside the list); 1500 / 700 / 300 take the
+    16 / 8 / 4 keys-per-thread register networks with +inf padding."""
     rng = np.random.default_rng(31)
-    n = 5200
     scene = dict(means3D=(rng.normal(0, 0.05, (n, 3))).astype(np.float32),
                  scales=np.full((n, 3), 0.6, np.float32) * rng.uniform(0.8, 1.2, (n, 3)).astype(np.float32),
                  rotations=np.tile(np.array([[1, 0, 0, 0]], np.float32), (n, 1)),
@@ -185,3 +186,24 @@ def test_odd_width_and_degenerate_inputs():
     cam = synth.make_camera(synth.look_at((0.5, 0.2, -3.0)), 131, 77, 120.0, 110.0)
     m = parity.compare(scene, [cam], 77, 131, 0, (0.3, 0.3, 0.3))
     parity.assert_parity(m, allow_flips=2)
+
+
+def test_repeated_backward_and_staged_forward_reuse_the_work_queues():
+    """The device-side work queues rewind themselves (no memset in the stream): a second backward on the same state,
+    and a forward issued one stage per call, give the results of the plain path."""
+    dev = torch.device("cuda:0")
+    sc = synth.random_scene(3000, seed=41)
+    t = {k: torch.tensor(v, device=dev) for k, v in sc.items()}
+    cam = torch.tensor(engine.pack_cameras_numpy([synth.front_camera(160, 128)]), device=dev)
+    kw = dict(colors_precomp=t["colors_precomp"], scales=t["scales"], rotations=t["rotations"])
+    a = engine.forward(t["means3D"], t["opacities"], cam, 128, 160, **kw)
+    b = engine.forward(t["means3D"], t["opacities"], cam, 128, 160, stage_events={}, **kw)
+    for k in range(4):
+        assert torch.equal(a[k], b[k])
+    gc = torch.randn_like(a[0])
+    g1 = engine.backward(a[4], gc).flat.clone()
+    g2 = engine.backward(a[4], gc).flat.clone()
+    g3 = engine.backward(b[4], gc, stage_events={}).flat.clone()
+    tol = 1e-5 * float(g1.abs().max())
+    assert float(g1.abs().max()) > 0
+    assert torch.allclose(g1, g2, rtol=1e-4, atol=tol) and torch.allclose(g1, g3, rtol=1e-4, atol=tol)

@@ -92,11 +92,13 @@ extern "C" size_t gs_workspace_bytes(int32_t N, int32_t V, int32_t H, int32_t W,
 // preprocess + tile histogram + scan: everything up to knowing the instance count
 static int run_front(const GsProblem* p, const GsParams& q, const GsLayout& L, int32_t* radii, cudaStream_t s)
 {
-    CK(cudaMemsetAsync(q.status, 0, sizeof(GsStatusDev), s));
-    CK(cudaMemsetAsync(q.tile_count, 0, 4 * (size_t)(L.total_tiles + 1), s));
+    // ONE memset: the status block (work-queue cursors included) and the tile histogram are adjacent in the workspace
+    static_assert(sizeof(GsStatusDev) <= 256, "status block must fit its 256-byte slot");
+    if (L.off_status != 0 || L.off_tile_count != 256) return GS_E_BAD_ARGS;
+    CK(cudaMemsetAsync(q.status, 0, L.off_tile_count + 4 * (size_t)(L.total_tiles + 1), s));
     gs_launch_preprocess(q, radii, s);
     CK_LAUNCH("preprocess_kernel");
-    gs_launch_tile_scan(q, s);
+    gs_launch_tile_scan(q, sm_count(), s);
     CK_LAUNCH("tile_scan");
     return 0;
 }
@@ -135,12 +137,10 @@ extern "C" int gs_forward_stages(const GsProblem* p, const GsForwardOut* out, ui
     }
     const int sms = sm_count();
     if (stages & GS_FWD_SORT) {
-        CK(cudaMemsetAsync(&q.status->q_sort, 0, sizeof(unsigned int), s));
         gs_launch_sort_gather(q, sms, s);
         CK_LAUNCH("sort_gather_kernel");
     }
     if (stages & GS_FWD_BLEND) {
-        CK(cudaMemsetAsync(&q.status->q_fwd_heavy, 0, 2 * sizeof(unsigned int), s));     // both forward queues
         gs_launch_blend_fwd(q, out->color, out->depth, out->alpha, sms, s);
         CK_LAUNCH("blend_fwd_kernel");
     }
@@ -165,7 +165,6 @@ extern "C" int gs_backward_stages(const GsProblem* p, const GsBackwardIO* io, ui
     const GsLayout L = gs_make_layout(p->N, p->V, p->H, p->W, p->cap_instances);
     const GsParams q = make_params(p, L);
     if (stages & GS_BWD_BLEND) {
-        CK(cudaMemsetAsync(&q.status->q_bwd_heavy, 0, sizeof(unsigned int), s));
         CK(cudaMemsetAsync(q.grad2d, 0, 48 * (size_t)p->V * p->N, s));
         gs_launch_blend_bwd(q, *io, sm_count(), s);
         CK_LAUNCH("blend_bwd_kernel");

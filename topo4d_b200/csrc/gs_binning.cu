@@ -61,16 +61,58 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const GsParam
     }
 }
 
-// phase B: exclusive scan of every block's chunk, offset by the sum of the preceding blocks
+// phase B: exclusive scan of every block's chunk, offset by the sum of the preceding blocks.
+// FUSED = true: phases A and B in ONE launch.  Every block publishes its total, then waits until all blocks have
+// (a grid-wide counter in the status block); legal because the launcher only picks this variant when the whole
+// grid is co-resident (scan_blocks <= SM count, one 1024-thread block per SM always fits).
+template <bool FUSED>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const GsParams p)
 {
     __shared__ unsigned long long s_red[32];
     __shared__ uint32_t s_warp[32];
     __shared__ unsigned long long s_prefix;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (FUSED) {
+        __shared__ uint32_t s_sum[32];
+        __shared__ uint32_t s_max[32];
+        const long long n0 = p.total_tiles;
+        const long long base0 = (long long)blockIdx.x * GS_SCAN_ELEMS_PER_BLOCK + threadIdx.x * SCAN_ITEMS;
+        uint32_t sum = 0, mx = 0;
+        #pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const long long e = base0 + k;
+            const uint32_t c = e < n0 ? p.tile_count[e] : 0u;
+            sum += c; mx = max(mx, c);
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) { s_sum[w] = sum; s_max[w] = mx; }
+        __syncthreads();
+        if (w == 0) {
+            sum = s_sum[lane]; mx = s_max[lane];
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (lane == 0) {
+                p.block_sums[blockIdx.x] = sum;
+                atomicMax(&p.status->max_tile_instances, (int)mx);
+                __threadfence();
+                atomicAdd(&p.status->scan_done, 1u);
+                volatile unsigned int* done = &p.status->scan_done;
+                while (*done < gridDim.x) { }
+                __threadfence();
+            }
+        }
+        __syncthreads();
+    }
     // prefix of preceding blocks (64-bit so an overflowing total is detected, not wrapped)
     unsigned long long pre = 0;
-    for (int b = threadIdx.x; b < (int)blockIdx.x; b += SCAN_THREADS) pre += p.block_sums[b];
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += SCAN_THREADS) pre += __ldcg(p.block_sums + b);
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
     if (lane == 0) s_red[w] = pre;
@@ -140,26 +182,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const GsParams
 }
 
 // ---- K4 ----
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_SMEM_KEYS = 4096;   // 32 KB of 64-bit keys; longer lists are sorted in place in global memory
+constexpr int SORT_THREADS = 128;
+constexpr int SORT_REG_KEYS = 2048;    // lists up to here are sorted in registers (<= 16 keys per thread); longer ones in place in HBM/L2
 
-// Bitonic network in the "flip / disperse" form: every compare-exchange moves the smaller key to the
-// lower index, so virtual +inf padding above `n` never moves and arbitrary n needs no real padding.
-// A stage whose partner distance is <= 32 only moves keys inside 64-element windows that one warp owns (thread t
-// and its 31 warp mates cover pair indices of the same window in every such stage), so between two such stages a
-// __syncwarp() is enough; only stages that cross windows pay a __syncthreads().
-__device__ __forceinline__ void stage_sync(bool local) { if (local) __syncwarp(); else __syncthreads(); }
-
+// Generic bitonic network in the "flip / disperse" form on a key array in memory (used only for lists longer than
+// SORT_REG_KEYS): every compare-exchange moves the smaller key to the lower index, so virtual +inf padding above `n`
+// never moves and arbitrary n needs no real padding.
 template <typename KeyPtr>
-__device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nthreads)
+__device__ __forceinline__ void bitonic_sort_mem(KeyPtr keys, int n, int tid, int nthreads)
 {
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
     const int half = n2 >> 1;
-    // every block size / partner distance is a power of two: index arithmetic is shifts and masks only
     for (int lk = 1; (1 << lk) <= n2; lk++) {
         const int k = 1 << lk, hk = k >> 1;
-        // flip: partner is the mirror position inside the k-block
         for (int t = tid; t < half; t += nthreads) {
             const int blk = t >> (lk - 1), off = t & (hk - 1);
             const int i = (blk << lk) + off, j = (blk << lk) + (k - 1 - off);
@@ -168,8 +204,7 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nt
                 if (a > b) { keys[i] = b; keys[j] = a; }
             }
         }
-        // next stage: jj = k/4 if it exists, else the flip of 2k
-        stage_sync(k <= 64 && ((k >> 2) > 0 ? true : (2 * k <= 64)));
+        __syncthreads();
         for (int lj = lk - 2; lj >= 0; lj--) {
             const int jj = 1 << lj;
             for (int t = tid; t < half; t += nthreads) {
@@ -179,9 +214,84 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nt
                     if (a > b) { keys[i] = b; keys[j] = a; }
                 }
             }
-            const bool next_local = lj > 0 ? true : (2 * k <= 64);   // next is jj/2 (local if this one is) or flip(2k)
-            stage_sync(jj <= 32 && next_local);
+            __syncthreads();
         }
+    }
+}
+
+// Register-resident bitonic sort of 128 * KPT keys by one 128-thread CTA: thread t owns positions [t*KPT, (t+1)*KPT).
+// Partner distances < KPT are compare-exchanges between a thread's own registers, distances < 32*KPT one
+// shuffle-xor per key, and only the two largest distances (3 of the ~50 steps) cross warps through shared memory.
+// Keys past the list end are +inf in registers, so the textbook network (direction bit = position & block size)
+// needs no memory padding.  Fully unrolled: every distance / direction test is an immediate.
+__host__ __device__ constexpr int ilog2_c(int x) { return x <= 1 ? 0 : 1 + ilog2_c(x >> 1); }
+
+__device__ __forceinline__ void cex(unsigned long long& a, unsigned long long& b, bool asc)
+{
+    const bool sw = (a > b) == asc;
+    const unsigned long long lo = sw ? b : a, hi = sw ? a : b;
+    a = lo; b = hi;
+}
+
+template <int KPT>
+__device__ __forceinline__ void bitonic_sort_regs(unsigned long long (&key)[KPT], int tid, unsigned long long* s_x)
+{
+    constexpr int LOGK = ilog2_c(KPT), LOGN = LOGK + 7;
+    #pragma unroll
+    for (int lk = 1; lk <= LOGN; lk++) {
+        #pragma unroll
+        for (int lj = lk - 1; lj >= 0; lj--) {
+            if (lj < LOGK) {
+                #pragma unroll
+                for (int a = 0; a < KPT; a++) {
+                    if ((a & (1 << lj)) == 0) {
+                        bool asc;
+                        if (lk == LOGN) asc = true;
+                        else if (lk < LOGK) asc = ((a >> lk) & 1) == 0;
+                        else asc = ((tid >> (lk - LOGK)) & 1) == 0;
+                        cex(key[a], key[a | (1 << lj)], asc);
+                    }
+                }
+            } else {
+                const int m = 1 << (lj - LOGK);                       // partner thread = tid ^ m
+                const bool asc = lk == LOGN ? true : ((tid >> (lk - LOGK)) & 1) == 0;
+                const bool take_min = asc == ((tid & m) == 0);
+                if (lj < LOGK + 5) {
+                    #pragma unroll
+                    for (int a = 0; a < KPT; a++) {
+                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key[a], m);
+                        key[a] = ((o < key[a]) == take_min) ? o : key[a];
+                    }
+                } else {
+                    #pragma unroll
+                    for (int a = 0; a < KPT; a++) s_x[a * SORT_THREADS + tid] = key[a];
+                    __syncthreads();
+                    #pragma unroll
+                    for (int a = 0; a < KPT; a++) {
+                        const unsigned long long o = s_x[a * SORT_THREADS + (tid ^ m)];
+                        key[a] = ((o < key[a]) == take_min) ? o : key[a];
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+    }
+}
+
+template <int KPT>
+__device__ __forceinline__ void sort_tile_regs(const unsigned long long* __restrict__ gk, int n, int tid, unsigned long long* s_keys)
+{
+    unsigned long long key[KPT];
+    #pragma unroll
+    for (int a = 0; a < KPT; a++) {
+        const int i = tid * KPT + a;
+        key[a] = i < n ? gk[i] : ~0ull;
+    }
+    bitonic_sort_regs<KPT>(key, tid, s_keys);
+    #pragma unroll
+    for (int a = 0; a < KPT; a++) {
+        const int i = tid * KPT + a;
+        if (i < n) s_keys[i] = key[a];
     }
     __syncthreads();
 }
@@ -189,30 +299,41 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr keys, int n, int tid, int nt
 // which of the tile's eight 8x4 pixel blocks can this splat reach at all?  Exact up to a safety margin: the minimum
 // of q(d) = 1/2 d^T conic d over the block's (continuous) rectangle against tau = -thr (thr already carries its own
 // margin).  q is convex, so the minimum is 0 if the centre is inside, else it lies on one of the four edges (a 1-D
-// clamped parabola each).  The blend kernels skip a block whose bit is clear without evaluating a single pixel; a
-// clear bit can never hide a contributor.
+// clamped parabola each).  The tile has only 4 distinct vertical and 8 distinct horizontal block edges: the per-line
+// terms are computed once and shared by the blocks along the line.  The blend kernels skip a block whose bit is
+// clear without evaluating a single pixel; a clear bit can never hide a contributor.
 __device__ __forceinline__ unsigned block_reach_mask(const float4 g0, const float4 g1, float tx0, float ty0)
 {
     const float A = g0.z, B = g0.w, C = g1.x, tau = -g1.w;
     if (!(A > 0.0f && C > 0.0f && A * C - B * B > 0.0f && tau < 3.0e38f)) return 0xffu;
     if (!(tau >= 0.0f)) return 0u;
-    unsigned mask = 0u;
     const float lim = tau * 1.0001f + 2.0e-3f;
-    const float nBC = -B / C, nBA = -B / A;
+    const float nBC = -B / C, nBA = -B / A, hA = 0.5f * A, hC = 0.5f * C;
+    // d = centre - pixel.  Column c of blocks spans dx in [X[2c+1], X[2c]], row r spans dy in [Y[2r+1], Y[2r]].
+    float X[4], Y[8], vq0[4], vq1[4], vs[4], hq0[8], hq1[8], hs[8];
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        X[i] = g0.x - (tx0 + (float)(8 * (i >> 1) + 7 * (i & 1)));
+        vq0[i] = hA * X[i] * X[i]; vq1[i] = B * X[i]; vs[i] = nBC * X[i];      // q(X, t) = vq0 + t (hC t + vq1), argmin t = vs
+    }
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        Y[i] = g0.y - (ty0 + (float)(4 * (i >> 1) + 3 * (i & 1)));
+        hq0[i] = hC * Y[i] * Y[i]; hq1[i] = B * Y[i]; hs[i] = nBA * Y[i];      // q(t, Y) = hq0 + t (hA t + hq1), argmin t = hs
+    }
+    unsigned mask = 0u;
     #pragma unroll
     for (int b = 0; b < 8; b++) {
-        const float bx0 = tx0 + 8.0f * (b & 1), by0 = ty0 + 4.0f * (b >> 1);
-        const float dx0 = g0.x - (bx0 + 7.0f), dx1 = g0.x - bx0;       // d = centre - pixel
-        const float dy0 = g0.y - (by0 + 3.0f), dy1 = g0.y - by0;
+        const int c = b & 1, r = b >> 1;
+        const float dx1 = X[2 * c], dx0 = X[2 * c + 1], dy1 = Y[2 * r], dy0 = Y[2 * r + 1];
         float qmin = 3.0e38f;
         #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const float ex = e ? dx1 : dx0;                            // vertical edges: dx fixed
-            const float ty = fminf(fmaxf(nBC * ex, dy0), dy1);
-            qmin = fminf(qmin, 0.5f * (A * ex * ex + C * ty * ty) + B * ex * ty);
-            const float ey = e ? dy1 : dy0;                            // horizontal edges: dy fixed
-            const float tx = fminf(fmaxf(nBA * ey, dx0), dx1);
-            qmin = fminf(qmin, 0.5f * (A * tx * tx + C * ey * ey) + B * tx * ey);
+            const int vi = 2 * c + e, hi = 2 * r + e;
+            const float ty = fminf(fmaxf(vs[vi], dy0), dy1);
+            qmin = fminf(qmin, fmaf(ty, fmaf(hC, ty, vq1[vi]), vq0[vi]));
+            const float tx = fminf(fmaxf(hs[hi], dx0), dx1);
+            qmin = fminf(qmin, fmaf(tx, fmaf(hA, tx, hq1[hi]), hq0[hi]));
         }
         if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) qmin = 0.0f;
         if (qmin <= lim) mask |= 1u << b;
@@ -220,9 +341,9 @@ __device__ __forceinline__ unsigned block_reach_mask(const float4 g0, const floa
     return mask;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParams p)
+__global__ void __launch_bounds__(SORT_THREADS, 8) sort_gather_kernel(const GsParams p)
 {
-    __shared__ unsigned long long s_keys[SORT_SMEM_KEYS];
+    __shared__ __align__(16) unsigned long long s_keys[SORT_REG_KEYS];
     __shared__ long long s_tile;
     const int tid = threadIdx.x;
     // non-empty tiles come from the device-side queue the scan kernel filled (dynamic load balance)
@@ -240,15 +361,13 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParam
         const int n = (int)(end - start);
         const int v = (int)(tg / p.tiles);
         unsigned long long* gk = p.pairs + start;
-        unsigned long long* sorted;
-        if (n <= SORT_SMEM_KEYS) {
-            for (int t = tid; t < n; t += SORT_THREADS) s_keys[t] = gk[t];
-            __syncthreads();
-            if (n > 1) bitonic_sort(s_keys, n, tid, SORT_THREADS);
-            sorted = s_keys;
-        } else {
-            __syncthreads();
-            bitonic_sort(gk, n, tid, SORT_THREADS);     // in place in L2-resident global memory
+        unsigned long long* sorted = s_keys;
+        if (n <= 128 * 2) sort_tile_regs<2>(gk, n, tid, s_keys);
+        else if (n <= 128 * 4) sort_tile_regs<4>(gk, n, tid, s_keys);
+        else if (n <= 128 * 8) sort_tile_regs<8>(gk, n, tid, s_keys);
+        else if (n <= 128 * 16) sort_tile_regs<16>(gk, n, tid, s_keys);
+        else {
+            bitonic_sort_mem(gk, n, tid, SORT_THREADS);     // in place in L2-resident global memory
             sorted = gk;
         }
         const float4* __restrict__ geom = p.geom + (size_t)v * p.N * 3;
@@ -257,6 +376,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParam
         const float tx0 = (float)((tl % p.tiles_x) * GS_TILE), ty0 = (float)((tl / p.tiles_x) * GS_TILE);
         // one thread per instance: Gaussian index out, block-reach mask into bits 24..31 of the key's low word
         // (indices are < 2^24, validated on the host)
+        #pragma unroll 2
         for (int k = tid; k < n; k += SORT_THREADS) {
             const unsigned long long key = sorted[k];
             const uint32_t id = (uint32_t)key & 0x00ffffffu;
@@ -266,6 +386,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParam
         }
         __syncthreads();
         // gather: 3 x 16 bytes per record, coalesced writes
+        #pragma unroll 4
         for (int t = tid; t < n * 3; t += SORT_THREADS) {
             const int k = t / 3, part = t - k * 3;
             const uint32_t low = (uint32_t)sorted[k];
@@ -275,14 +396,19 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_gather_kernel(const GsParam
         }
         __syncthreads();   // s_keys is reused by the next tile
     }
+    if (tid == 0) gs_queue_release(&p.status->q_sort, &p.status->done_sort, gridDim.x);
 }
 
 }  // namespace
 
-void gs_launch_tile_scan(const GsParams& p, cudaStream_t s)
+void gs_launch_tile_scan(const GsParams& p, int num_sms, cudaStream_t s)
 {
-    scan_reduce_kernel<<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
-    scan_write_kernel<<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
+    if (p.scan_blocks <= num_sms) {             // whole grid co-resident: one launch (see scan_write_kernel<true>)
+        scan_write_kernel<true><<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
+    } else {
+        scan_reduce_kernel<<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
+        scan_write_kernel<false><<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
+    }
 }
 
 void gs_launch_sort_gather(const GsParams& p, int num_sms, cudaStream_t s)

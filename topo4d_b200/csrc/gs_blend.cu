@@ -353,6 +353,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
         }
         __syncwarp();
     }
+    if (lane == 0) gs_queue_release(&p.status->q_fwd_heavy, &p.status->done_fwd, gridDim.x * WPC, &p.status->q_fwd_fill);
 }
 
 template <int PX>
@@ -547,6 +548,7 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
         }
         __syncwarp();
     }
+    if (lane == 0) gs_queue_release(&p.status->q_bwd_heavy, &p.status->done_bwd, gridDim.x * WPC);
 }
 
 int resident_ctas(const void* kernel, int block, int num_sms, int fallback_per_sm)

@@ -43,6 +43,9 @@ struct GsStatusDev {
     unsigned int q_bwd_heavy;           // next index into active_tiles[] (backward)
     unsigned int q_sort;                // next index into active_tiles[] (sort + gather)
     unsigned int num_short;             // the other non-empty tiles: active_tiles[total_tiles-1 .. ] downwards
+    // (the first 48 bytes above are mirrored by the host layer; everything below is device-only)
+    unsigned int scan_done;             // blocks of the fused tile scan that have published their total
+    unsigned int done_sort, done_fwd, done_bwd;   // workers that have left a queue: the last one rewinds its cursor(s)
 };
 #define GS_LONG_TILE 384                // longest-first work order: long lists are handed out before short ones
 #define GS_FILL_GROUP 16
@@ -117,7 +120,7 @@ struct GsParams {
 void gs_launch_preprocess(const GsParams& p, int32_t* radii, cudaStream_t s);
 void gs_launch_scatter(const GsParams& p, const int32_t* radii, cudaStream_t s);
 void gs_launch_mark_visible(int N, const float* means3D, const float* cam, uint8_t* visible, cudaStream_t s);
-void gs_launch_tile_scan(const GsParams& p, cudaStream_t s);
+void gs_launch_tile_scan(const GsParams& p, int num_sms, cudaStream_t s);
 void gs_launch_sort_gather(const GsParams& p, int num_sms, cudaStream_t s);
 void gs_launch_blend_fwd(const GsParams& p, float* color, float* depth, float* alpha, int num_sms, cudaStream_t s);
 void gs_launch_blend_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms, cudaStream_t s);
@@ -132,6 +135,19 @@ __device__ __forceinline__ long long gs_active_tile(const GsParams& p, unsigned 
     const unsigned j = i - nl;
     if (j < ns) return (long long)p.active_tiles[p.total_tiles - 1 - j];
     return -1;
+}
+
+// Self-cleaning work queues: a worker calls this once, after its last fetch came back empty.  The last of the
+// `workers` to arrive rewinds the cursor (and the arrival counter), so the next launch on the same workspace --
+// a repeated backward, a staged re-run -- starts from zero without a memset in the stream.
+__device__ __forceinline__ void gs_queue_release(unsigned int* cursor, unsigned int* done, unsigned int workers, unsigned int* cursor2 = nullptr)
+{
+    __threadfence();
+    if (atomicAdd(done, 1u) == workers - 1u) {
+        *cursor = 0u;
+        if (cursor2) *cursor2 = 0u;
+        *done = 0u;
+    }
 }
 
 // ---- mbarrier + bulk async copy (TMA-family, SASS: UBLKCP / SYNCS) ----

@@ -45,7 +45,7 @@ def pick_blend_px(num_active_tiles: int | None) -> int:
     there are few (more warps per tile: the per-tile latency bounds such launches).  Never changes results."""
     if num_active_tiles is None or num_active_tiles >= 20000:
         return 4
-    return 2 if num_active_tiles >= 3000 else 1
+    return 2 if num_active_tiles >= 1200 else 1
 
 
 def _ptr(t: torch.Tensor | None):
