@@ -16,6 +16,11 @@
  *       inputs built at helpers.py:91-112.
  *   gs_mark_visible ........... `_C.mark_visible` behind `GaussianRasterizer.markVisible`
  *       (API completeness; Topo4D never calls it).
+ *   t4d_image_loss ............ the per-iteration image loss and its autograd backward:
+ *       `exp(cam_m)*im + cam_c` (train.py:310), `0.8*l1_loss_v1 + 0.2*(1 - calc_ssim)` (train.py:317;
+ *       helpers.py:115-116, external.py:71-116), and loss.backward() down to dL/d(rendered image).
+ *   t4d_adam_step ............. `optimizer.step()` of torch.optim.Adam(param_groups, lr=0.0, eps=1e-15)
+ *       (train.py:272-297, 672) fused with the boolean-mask overwrites that follow it (train.py:676-700).
  *   f3d_render_colors[_host] .. `_render_colors_core` (face3d/mesh/cython/mesh_core.cpp:169-234)
  *       as bound by `render_colors_core` (face3d/mesh/cython/mesh_core_cython.pyx:64-77) and
  *       reached through face3d/mesh/render.py:52-86 from helpers.py:956.
@@ -184,6 +189,42 @@ int f3d_render_colors(float* image, const float* vertices, const int32_t* triang
                       void* workspace, size_t workspace_bytes, gs_stream_t stream);
 /* Optional fused epilogue of helpers.py:959: out_u8[h,w,c] = (uint8)(image*255) (C truncation). */
 int f3d_image_to_u8(const float* image, uint8_t* out_u8, int64_t count, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimisation-loop tail: image loss forward+backward, fused Adam.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct T4dImageLoss {
+    int32_t V, H, W;                /* views in this call (the reference: 1), image size                       */
+    float   w_l1, w_ssim;           /* train.py:317: 0.8 and 0.2 (times any outer loss weight)                 */
+    const float* render;            /* [V,3,H,W] rasterizer output, BEFORE the per-camera affine               */
+    const float* target;            /* [V,3,H,W] ground-truth frame (curr_data['im'])                          */
+    const float* cam_m;             /* [V,3] or NULL: im = exp(cam_m) * render + cam_c (train.py:310); both or neither */
+    const float* cam_c;             /* [V,3] or NULL                                                           */
+    float*  loss;                   /* out [V,4]: mean|im-gt|, mean SSIM, w_l1*l1 + w_ssim*(1-ssim), 0          */
+    float*  dL_drender;             /* out [V,3,H,W]: d(sum over views of loss[v][2]) / d render; NULL = forward only */
+    float*  dL_dcam_m;              /* out [V,3] or NULL                                                       */
+    float*  dL_dcam_c;              /* out [V,3] or NULL                                                       */
+    void*   workspace;              /* t4d_image_loss_workspace_bytes(V,H,W) bytes, 256-byte aligned, device   */
+    size_t  workspace_bytes;
+} T4dImageLoss;
+size_t t4d_image_loss_workspace_bytes(int32_t V, int32_t H, int32_t W);
+int t4d_image_loss(const T4dImageLoss* p, gs_stream_t stream);
+
+#define T4D_ADAM_MAX_SEGMENTS 24
+typedef struct T4dAdamSegment {    /* one named parameter = one torch param group (train.py:290-294)            */
+    float*  param;                  /* [count] updated in place                                                 */
+    const float* grad;              /* [count]                                                                  */
+    float*  exp_avg;                /* [count] Adam first moment (state['exp_avg'])                             */
+    float*  exp_avg_sq;             /* [count] second moment                                                    */
+    const uint8_t* pin_mask;        /* [count/row_width] or NULL: rows overwritten after the step (train.py:676-700) */
+    const float* pin_values;        /* [count] values for pinned rows; NULL = zeros                             */
+    int64_t count;
+    int32_t row_width;              /* elements per row (3 for means3D / colours / scales, 4 rotations, 1 opacities) */
+    int32_t step;                   /* 1-based step count of this parameter (state['step'] after increment)     */
+    float   lr;                     /* the group's current learning rate (update_optimizer, helpers.py:801-804) */
+} T4dAdamSegment;
+/* `segments` is a HOST array; betas/eps as in torch.optim.Adam (reference: 0.9, 0.999, 1e-15). */
+int t4d_adam_step(const T4dAdamSegment* segments, int32_t nseg, float beta1, float beta2, float eps, gs_stream_t stream);
 
 #ifdef __cplusplus
 }

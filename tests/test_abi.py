@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_functions():
     src = open(os.path.join(ROOT, "include", "topo4d_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:gs|f3d)_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b((?:gs|f3d|t4d)_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_all_exported_and_bound():

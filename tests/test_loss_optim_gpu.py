@@ -1,0 +1,174 @@
+"""GPU parity of the fused image loss (csrc/t4d_loss.cu) and fused Adam (csrc/t4d_optim.cu) through the C ABI.
+
+Oracle: oracle/loss_oracle.py (float64 restatement of external.py:71-116, helpers.py:115-116, train.py:310,317,
+torch.optim.Adam), itself pinned to the reference's own outputs in tests/golden/{loss,adam}.npz.
+Tolerances (floating point; the kernels compute in fp32): loss terms 1e-5 absolute; gradients 1e-3 relative
+(|d| / (|ref| + 1e-3 max|ref|)), the bar BASELINE.json states for gradients -- measured ~1e-5.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_oracle
+from topo4d_b200 import losses, optim
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda:0"
+
+
+def rel_err(a, ref):
+    a = np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.max(np.abs(a - ref) / (np.abs(ref) + 1e-3 * np.max(np.abs(ref)) + 1e-30)))
+
+
+def run_gpu(render, target, cam_m=None, cam_c=None, w_l1=0.8, w_ssim=0.2):
+    r = torch.tensor(render, device=DEV, requires_grad=True)
+    t = torch.tensor(target, device=DEV)
+    m = None if cam_m is None else torch.tensor(cam_m, device=DEV, requires_grad=True)
+    c = None if cam_c is None else torch.tensor(cam_c, device=DEV, requires_grad=True)
+    total, terms = losses.image_loss(r, t, m, c, w_l1, w_ssim, return_terms=True)
+    total.backward()
+    out = {"total": total.item(), "terms": terms.cpu().numpy(), "d_render": r.grad.cpu().numpy()}
+    if m is not None:
+        out["d_cam_m"], out["d_cam_c"] = m.grad.cpu().numpy(), c.grad.cpu().numpy()
+    return out
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_image_loss_matches_reference_golden(name):
+    g = np.load(os.path.join(G, "loss.npz"))
+    affine = bool(g[name + "_affine"])
+    o = run_gpu(g[name + "_render"], g[name + "_target"], g[name + "_cam_m"] if affine else None, g[name + "_cam_c"] if affine else None)
+    np.testing.assert_allclose(o["terms"][0, :3], g[name + "_terms"], rtol=0, atol=1e-5)
+    assert abs(o["total"] - g[name + "_terms"][2]) < 1e-5
+    assert rel_err(o["d_render"], g[name + "_d_render"]) < 1e-3
+    if affine:
+        assert rel_err(o["d_cam_m"], g[name + "_d_cam_m"]) < 1e-3 and rel_err(o["d_cam_c"], g[name + "_d_cam_c"]) < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(1, 135, 240), (3, 67, 33), (2, 1, 1), (1, 5, 300)])
+def test_image_loss_matches_oracle_on_random_batches(shape):
+    """Multi-view batches, ragged tiles (sizes not multiples of 32), images smaller than the 11-tap window."""
+    v, h, w = shape
+    rng = np.random.default_rng(h * w)
+    render = rng.uniform(0, 1, (v, 3, h, w)).astype(np.float32)
+    target = np.clip(0.6 * render + 0.4 * rng.uniform(0, 1, render.shape), 0, 1).astype(np.float32)
+    cam_m = rng.normal(0, 0.1, (v, 3)).astype(np.float32)
+    cam_c = rng.normal(0, 0.05, (v, 3)).astype(np.float32)
+    ref = loss_oracle.image_loss(render, target, cam_m, cam_c)
+    o = run_gpu(render, target, cam_m, cam_c)
+    np.testing.assert_allclose(o["terms"][:, :3], ref["terms"][:, :3], rtol=0, atol=1e-5)
+    assert abs(o["total"] - ref["terms"][:, 2].sum()) < 1e-5 * v
+    for k in ("d_render", "d_cam_m", "d_cam_c"):
+        assert rel_err(o[k], ref[k]) < 1e-3, k
+
+
+def test_full_size_properties_1080p():
+    """BASELINE size (1080p): identical images -> L1 0, SSIM 1, zero gradient; weights are linear; the drop-in
+    l1_loss_v1 / calc_ssim agree with the reference formulas evaluated by PyTorch in fp32 on the same device."""
+    torch.manual_seed(0)
+    x = torch.rand(3, 1080, 1920, device=DEV)
+    y = (0.7 * x + 0.3 * torch.rand_like(x)).clamp(0, 1)
+    xr = x.clone().requires_grad_(True)
+    total, terms = losses.image_loss(xr, x, return_terms=True)
+    total.backward()
+    assert abs(terms[0, 0].item()) < 1e-7 and abs(terms[0, 1].item() - 1.0) < 1e-6 and abs(total.item()) < 1e-6
+    assert float(xr.grad.abs().max()) < 1e-9
+    # linearity in the weights: L(0.8, 0.2) = 0.8 L(1, 0) + 0.2 L(0, 1), values and gradients
+    def lg(w1, w2):
+        r = x.clone().requires_grad_(True)
+        l = losses.image_loss(r, y, None, None, w1, w2)
+        l.backward()
+        return l.item(), r.grad
+    l_a, g_a = lg(0.8, 0.2)
+    l_b, g_b = lg(1.0, 0.0)
+    l_c, g_c = lg(0.0, 1.0)
+    assert abs(l_a - (0.8 * l_b + 0.2 * l_c)) < 1e-6
+    assert torch.allclose(g_a, 0.8 * g_b + 0.2 * g_c, rtol=1e-4, atol=1e-12)
+    # drop-in names against the reference formulas in plain PyTorch (fp32, same device)
+    l1 = losses.l1_loss_v1(x, y).item()
+    assert abs(l1 - torch.abs(x - y).mean().item()) < 1e-6
+    # (cuDNN would otherwise run these convolutions in TF32, 1e-3-accurate: the fp32 kernel must not be judged by it)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    win = loss_oracle.gaussian_window().float().to(DEV)
+    w2d = (win[:, None] @ win[None, :]).expand(3, 1, 11, 11).contiguous()
+    xt = x.clone().requires_grad_(True)
+    conv = lambda t: torch.nn.functional.conv2d(t[None], w2d, padding=5, groups=3)      # noqa: E731
+    mu1, mu2 = conv(xt), conv(y)
+    s1, s2, s12 = conv(xt * xt) - mu1 * mu1, conv(y * y) - mu2 * mu2, conv(xt * y) - mu1 * mu2
+    ssim_ref = (((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s1 + s2 + 9e-4))).mean()
+    ssim_ref.backward()
+    torch.backends.cudnn.allow_tf32 = tf32
+    xs = x.clone().requires_grad_(True)
+    ssim = losses.calc_ssim(xs, y)
+    ssim.backward()
+    assert abs(ssim.item() - ssim_ref.item()) < 1e-5
+    assert rel_err(xs.grad.cpu().numpy(), xt.grad.cpu().numpy()) < 1e-3
+
+
+def test_image_loss_argument_errors():
+    x = torch.rand(3, 8, 8, device=DEV)
+    with pytest.raises(ValueError):
+        losses.image_loss(x, x, torch.zeros(3, device=DEV), None)
+    with pytest.raises(ValueError):
+        losses.image_loss(torch.rand(4, 8, 8, device=DEV), torch.rand(4, 8, 8, device=DEV))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        losses.image_loss(x.cpu(), x.cpu())
+    with pytest.raises(NotImplementedError):
+        losses.calc_ssim(x, x, window_size=7)
+
+
+def test_fused_adam_matches_reference_golden_and_torch():
+    g = np.load(os.path.join(G, "adam.npz"))
+    lrs = {"means3D": 0.0, "rgb_colors": 0.0025, "unnorm_rotations": 0.001, "log_scales": 0.001, "cam_m": 1e-4}
+    params = {k: torch.nn.Parameter(torch.tensor(g[k + "_init"], device=DEV)) for k in lrs}
+    opt = optim.FusedAdam([{"params": [v], "name": k, "lr": lrs[k]} for k, v in params.items()], lr=0.0, eps=1e-15)
+    for s in range(int(g["steps"])):
+        if s == int(g["lr_change_step"]):
+            for grp in opt.param_groups:                         # update_optimizer, helpers.py:801-804
+                if grp["name"] == "means3D":
+                    grp["lr"] = 0.000016
+        for k, v in params.items():
+            v.grad = torch.tensor(g[k + "_grads"][s], device=DEV)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    for k, v in params.items():
+        np.testing.assert_allclose(v.detach().cpu().numpy(), g[k + "_final"], rtol=2e-6, atol=2e-7)
+        assert rel_err(opt.state[v]["exp_avg"].cpu().numpy(), g[k + "_exp_avg"]) < 5e-5
+        assert rel_err(opt.state[v]["exp_avg_sq"].cpu().numpy(), g[k + "_exp_avg_sq"]) < 5e-5
+
+
+def test_fused_adam_large_ragged_and_pinned_rows():
+    """A 60k x 48 SH-sized tensor, a ragged one (scalar tail path), pinned rows (train.py:676-700) -- against
+    torch.optim.Adam + index assignment on the same device."""
+    torch.manual_seed(1)
+    shapes = [(60000, 48), (1001, 3), (7,), (60000, 1)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    lrs = [0.0025, 0.001, 1e-4, 0.05]
+    ref = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(ref_p, lrs)], lr=0.0, eps=1e-15)
+    ours = optim.FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(our_p, lrs)], lr=0.0, eps=1e-15)
+    mask = torch.rand(1001, device=DEV) < 0.3
+    vals = torch.randn(1001, 3, device=DEV)
+    mask1 = torch.rand(60000, device=DEV) < 0.5
+    ours.pin(our_p[1], mask, vals)
+    ours.pin(our_p[3], mask1, None)
+    for s in range(5):
+        for a, b in zip(ref_p, our_p):
+            gr = torch.randn_like(a) * (10.0 ** (-s))
+            a.grad, b.grad = gr, gr.clone()
+        ref.step()
+        with torch.no_grad():
+            ref_p[1][mask] = vals[mask]
+            ref_p[3][mask1] = 0.0
+        ours.step()
+    for a, b in zip(ref_p, our_p):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert torch.equal(our_p[1][mask], vals[mask]) and float(our_p[3][mask1].abs().max()) == 0.0
+    sd = ours.state_dict()
+    assert len(sd["state"]) == 4 and sd["param_groups"][0]["lr"] == 0.0025

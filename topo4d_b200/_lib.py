@@ -47,6 +47,20 @@ class GsWorkspaceView(C.Structure):
                 ("final_T", _vp), ("n_contrib", _vp), ("grad2d", _vp), ("tiles_x", C.c_int32), ("tiles_y", C.c_int32)]
 
 
+class T4dImageLoss(C.Structure):
+    _fields_ = [("V", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("w_l1", C.c_float), ("w_ssim", C.c_float),
+                ("render", _vp), ("target", _vp), ("cam_m", _vp), ("cam_c", _vp), ("loss", _vp), ("dL_drender", _vp),
+                ("dL_dcam_m", _vp), ("dL_dcam_c", _vp), ("workspace", _vp), ("workspace_bytes", C.c_size_t)]
+
+
+T4D_ADAM_MAX_SEGMENTS = 24
+
+
+class T4dAdamSegment(C.Structure):
+    _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("pin_mask", _vp), ("pin_values", _vp),
+                ("count", C.c_int64), ("row_width", C.c_int32), ("step", C.c_int32), ("lr", C.c_float)]
+
+
 # every symbol include/topo4d_b200.h declares: (name, restype, argtypes)
 SYMBOLS = {
     "gs_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
@@ -64,6 +78,9 @@ SYMBOLS = {
     "f3d_render_colors": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     _vp, C.c_size_t, _vp]),
     "f3d_image_to_u8": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "t4d_image_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "t4d_image_loss": (C.c_int, [C.POINTER(T4dImageLoss), _vp]),
+    "t4d_adam_step": (C.c_int, [C.POINTER(T4dAdamSegment), C.c_int32, C.c_float, C.c_float, C.c_float, _vp]),
 }
 
 _LIB = None

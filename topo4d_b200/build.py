@@ -29,6 +29,8 @@ SOURCES = [
     ("gs_backward.cu", []),
     ("gs_api.cu", []),
     ("f3d_render.cu", ["--fmad=false"]),
+    ("t4d_loss.cu", []),
+    ("t4d_optim.cu", []),
 ]
 
 

@@ -1,0 +1,89 @@
+"""Fused Adam for Topo4D's parameter dictionary over the C ABI.
+
+Mirrors how the reference builds and drives its optimiser:
+  * ``torch.optim.Adam(param_groups, lr=0.0, eps=1e-15)`` with one group per named parameter, each with its own
+    ``lr`` and a ``name`` key (train.py:272-297), so ``update_optimizer`` (helpers.py:801-804), which edits
+    ``optimizer.param_groups[i]['lr']`` by name, works on this class unchanged;
+  * ``optimizer.step()`` / ``optimizer.zero_grad(set_to_none=True)`` once per iteration (train.py:672-673);
+  * the boolean-mask overwrites that follow every step (train.py:676-700) can be registered once with :meth:`pin`
+    and are then applied inside the same kernel launch.
+State layout is torch.optim.Adam's (``state[p]['step' | 'exp_avg' | 'exp_avg_sq']``), so ``state_dict`` round-trips.
+All parameters of one ``step()`` go through ONE launch of ``t4d_adam_step`` (csrc/t4d_optim.cu).  CUDA-only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        if lr < 0.0 or eps < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
+            raise ValueError("invalid Adam hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._pins: dict[int, tuple[torch.Tensor, torch.Tensor | None]] = {}
+        g0 = self.param_groups[0]
+        if any(g["betas"] != g0["betas"] or g["eps"] != g0["eps"] for g in self.param_groups):
+            raise ValueError("FusedAdam shares betas / eps across groups (as the reference does); only lr is per group")
+
+    def pin(self, param: torch.Tensor, mask: torch.Tensor, values: torch.Tensor | None = None) -> None:
+        """After every step, rows of `param` where `mask` (bool [rows]) is set are overwritten with the same rows of
+        `values` (same shape as `param`; None = zeros) -- the fused form of ``params[name][mask] = const``
+        (train.py:676-700).  Later calls for the same parameter replace the registration; ``mask=None`` removes it."""
+        if mask is None:
+            self._pins.pop(id(param), None)
+            return
+        rows = param.shape[0]
+        m = mask.to(device=param.device).reshape(rows).to(torch.uint8).contiguous()
+        v = None if values is None else values.to(device=param.device, dtype=torch.float32).expand_as(param).contiguous()
+        self._pins[id(param)] = (m, v)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        segs, keep = [], []
+        dev = None
+        for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise RuntimeError("topo4d_b200.FusedAdam is CUDA-only; there is no CPU path")
+                if p.dtype is not torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("FusedAdam needs contiguous fp32 parameters")
+                if dev is None:
+                    dev = p.device
+                elif p.device != dev:
+                    raise RuntimeError("FusedAdam: all parameters must live on one device")
+                grad = p.grad if (p.grad.is_contiguous() and p.grad.dtype is torch.float32) else p.grad.float().contiguous()
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] = int(st["step"]) + 1
+                pin = self._pins.get(id(p))
+                rw = int(p.numel() // p.shape[0]) if (pin is not None and p.dim() > 0 and p.shape[0] > 0) else 1
+                segs.append(_lib.T4dAdamSegment(p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                                                None if pin is None else pin[0].data_ptr(),
+                                                None if pin is None or pin[1] is None else pin[1].data_ptr(),
+                                                p.numel(), rw, st["step"], float(g["lr"])))
+                keep.append(grad)
+        if not segs:
+            return loss
+        b1, b2 = self.param_groups[0]["betas"]
+        eps = self.param_groups[0]["eps"]
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for i in range(0, len(segs), _lib.T4D_ADAM_MAX_SEGMENTS):
+                chunk = segs[i:i + _lib.T4D_ADAM_MAX_SEGMENTS]
+                arr = (_lib.T4dAdamSegment * len(chunk))(*chunk)
+                _lib.check(L.t4d_adam_step(arr, len(chunk), float(b1), float(b2), float(eps), stream), "t4d_adam_step")
+        return loss
