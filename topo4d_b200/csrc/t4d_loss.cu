@@ -22,6 +22,8 @@
 // enqueued back to back with no host round trip.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
+#include <string.h>
 #include "../../include/topo4d_b200.h"
 
 namespace {
@@ -32,7 +34,16 @@ constexpr int PITCH = 44;               // padded row pitch of the input planes 
 constexpr int THREADS = 256;
 constexpr float SSIM_C1 = 0.01f * 0.01f, SSIM_C2 = 0.03f * 0.03f;
 
-struct Win { float w[WIN]; };
+struct Win { float w[WIN]; unsigned long long ww[WIN]; };   // taps, and the same taps as packed (w, w) fp32 pairs
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2: one issue slot for two FMAs) ----
+// The five SSIM moments pair up naturally -- (x, y), (x^2, y^2) and xy alone -- so the window passes carry pairs in
+// 64-bit registers: 4 instructions per tap instead of 7 in the horizontal pass, 3 instead of 5 in the vertical one.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 struct LossParams {
     const float* render; const float* target; const float* cam_m; const float* cam_c;
@@ -70,9 +81,10 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* s_red)
 
 __global__ void __launch_bounds__(THREADS) ssim_fwd_kernel(const LossParams p)
 {
-    __shared__ __align__(16) float s_x[IN][PITCH];
-    __shared__ __align__(16) float s_y[IN][PITCH];
-    __shared__ __align__(16) float s_h[5][IN][TX];
+    __shared__ __align__(16) f32x2 s_xy[IN][PITCH];          // (x, y) pairs
+    __shared__ __align__(16) f32x2 s_h01[IN][TX];            // horizontal pass of (x, y)
+    __shared__ __align__(16) f32x2 s_h23[IN][TX];            //                    (x^2, y^2)
+    __shared__ __align__(16) float s_h4[IN][TX];             //                    xy
     __shared__ float2 s_red[THREADS / 32];
     const int tid = threadIdx.x;
     const int plane = blockIdx.z;
@@ -81,64 +93,94 @@ __global__ void __launch_bounds__(THREADS) ssim_fwd_kernel(const LossParams p)
     const float a = p.cam_m ? expf(p.cam_m[plane]) : 1.0f, b = p.cam_c ? p.cam_c[plane] : 0.0f;
     const float* __restrict__ rp = p.render + (size_t)plane * HW;
     const float* __restrict__ tp = p.target + (size_t)plane * HW;
+    const int tx = tid & 31, ty = tid >> 5;
 
     // the convolution pads the AFFINE image with zeros (conv2d padding=5 on `im`): outside pixels are x = y = 0
-    for (int idx = tid; idx < IN * IN; idx += THREADS) {
-        const int r = idx / IN, c = idx - r * IN;
-        const int gy = y0 - RAD + r, gx = x0 - RAD + c;
-        float x = 0.f, y = 0.f;
-        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-            x = fmaf(a, __ldg(rp + (size_t)gy * p.W + gx), b);
-            y = __ldg(tp + (size_t)gy * p.W + gx);
+    for (int r = ty; r < IN; r += THREADS / 32) {
+        const int gy = y0 - RAD + r;
+        const bool row_in = gy >= 0 && gy < p.H;
+        #pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int c = tx + 32 * cc;
+            if (c < IN) {
+                const int gx = x0 - RAD + c;
+                float x = 0.f, y = 0.f;
+                if (row_in && gx >= 0 && gx < p.W) {
+                    x = fmaf(a, __ldg(rp + (size_t)gy * p.W + gx), b);
+                    y = __ldg(tp + (size_t)gy * p.W + gx);
+                }
+                s_xy[r][c] = pk2(x, y);
+            }
         }
-        s_x[r][c] = x; s_y[r][c] = y;
     }
     __syncthreads();
 
-    // horizontal pass: strips of 4 adjacent outputs share a 14-wide register window of x and y
+    // horizontal pass: strips of 4 adjacent outputs share a 14-wide register window of (x, y) pairs
     for (int s = tid; s < IN * (TX / 4); s += THREADS) {
         const int r = s >> 3, c0 = (s & 7) * 4;
-        float vx[16], vy[16];
+        f32x2 v[14];
         #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float4 fx = *reinterpret_cast<const float4*>(&s_x[r][c0 + 4 * q]);
-            const float4 fy = *reinterpret_cast<const float4*>(&s_y[r][c0 + 4 * q]);
-            vx[4 * q] = fx.x; vx[4 * q + 1] = fx.y; vx[4 * q + 2] = fx.z; vx[4 * q + 3] = fx.w;
-            vy[4 * q] = fy.x; vy[4 * q + 1] = fy.y; vy[4 * q + 2] = fy.z; vy[4 * q + 3] = fy.w;
+        for (int q = 0; q < 7; q++) {
+            const ulonglong2 f = *reinterpret_cast<const ulonglong2*>(&s_xy[r][c0 + 2 * q]);
+            v[2 * q] = f.x; v[2 * q + 1] = f.y;
         }
-        float h[5][4];
+        f32x2 h01[4], h23[4];
+        float h4[4];
         #pragma unroll
         for (int o = 0; o < 4; o++) {
-            float hx = 0.f, hy = 0.f, hxx = 0.f, hyy = 0.f, hxy = 0.f;
+            f32x2 a01 = 0ull, a23 = 0ull;                       // (+0, +0)
+            float hxy = 0.f;
             #pragma unroll
             for (int k = 0; k < WIN; k++) {
-                const float w = p.win.w[k], px = vx[o + k], py = vy[o + k];
-                const float wx = w * px, wy = w * py;
-                hx += wx; hy += wy;
-                hxx = fmaf(wx, px, hxx); hyy = fmaf(wy, py, hyy); hxy = fmaf(wx, py, hxy);
+                const f32x2 pxy = v[o + k];
+                const f32x2 wp = mul2(p.win.ww[k], pxy);       // (w x, w y)
+                a01 = fma2(p.win.ww[k], pxy, a01);
+                a23 = fma2(wp, pxy, a23);
+                float wx, wy, px, py;
+                upk2(wp, wx, wy); upk2(pxy, px, py);
+                hxy = fmaf(wx, py, hxy);
             }
-            h[0][o] = hx; h[1][o] = hy; h[2][o] = hxx; h[3][o] = hyy; h[4][o] = hxy;
+            h01[o] = a01; h23[o] = a23; h4[o] = hxy;
         }
-        #pragma unroll
-        for (int q = 0; q < 5; q++)
-            *reinterpret_cast<float4*>(&s_h[q][r][c0]) = make_float4(h[q][0], h[q][1], h[q][2], h[q][3]);
+        *reinterpret_cast<ulonglong2*>(&s_h01[r][c0]) = make_ulonglong2(h01[0], h01[1]);
+        *reinterpret_cast<ulonglong2*>(&s_h01[r][c0 + 2]) = make_ulonglong2(h01[2], h01[3]);
+        *reinterpret_cast<ulonglong2*>(&s_h23[r][c0]) = make_ulonglong2(h23[0], h23[1]);
+        *reinterpret_cast<ulonglong2*>(&s_h23[r][c0 + 2]) = make_ulonglong2(h23[2], h23[3]);
+        *reinterpret_cast<float4*>(&s_h4[r][c0]) = make_float4(h4[0], h4[1], h4[2], h4[3]);
     }
     __syncthreads();
 
     // vertical pass: thread (tx, ty) owns 4 consecutive rows of column tx
-    const int tx = tid & 31, ty = tid >> 5;
     float m[5][4];
-    #pragma unroll
-    for (int q = 0; q < 5; q++) {
-        float v[14];
+    {
+        f32x2 v[14];
         #pragma unroll
-        for (int i = 0; i < 14; i++) v[i] = s_h[q][ty * 4 + i][tx];
+        for (int i = 0; i < 14; i++) v[i] = s_h01[ty * 4 + i][tx];
+        #pragma unroll
+        for (int o = 0; o < 4; o++) {
+            f32x2 acc = 0ull;
+            #pragma unroll
+            for (int k = 0; k < WIN; k++) acc = fma2(p.win.ww[k], v[o + k], acc);
+            upk2(acc, m[0][o], m[1][o]);
+        }
+        #pragma unroll
+        for (int i = 0; i < 14; i++) v[i] = s_h23[ty * 4 + i][tx];
+        #pragma unroll
+        for (int o = 0; o < 4; o++) {
+            f32x2 acc = 0ull;
+            #pragma unroll
+            for (int k = 0; k < WIN; k++) acc = fma2(p.win.ww[k], v[o + k], acc);
+            upk2(acc, m[2][o], m[3][o]);
+        }
+        float u[14];
+        #pragma unroll
+        for (int i = 0; i < 14; i++) u[i] = s_h4[ty * 4 + i][tx];
         #pragma unroll
         for (int o = 0; o < 4; o++) {
             float acc = 0.f;
             #pragma unroll
-            for (int k = 0; k < WIN; k++) acc = fmaf(p.win.w[k], v[o + k], acc);
-            m[q][o] = acc;
+            for (int k = 0; k < WIN; k++) acc = fmaf(p.win.w[k], u[o + k], acc);
+            m[4][o] = acc;
         }
     }
 
@@ -156,7 +198,9 @@ __global__ void __launch_bounds__(THREADS) ssim_fwd_kernel(const LossParams p)
             const float inv = 1.0f / (B1 * B2);
             const float S = (A1 * A2) * inv;
             ssim_sum += S;
-            l1_sum += fabsf(s_x[ty * 4 + o + RAD][tx + RAD] - s_y[ty * 4 + o + RAD][tx + RAD]);
+            float cx, cy;
+            upk2(s_xy[ty * 4 + o + RAD][tx + RAD], cx, cy);
+            l1_sum += fabsf(cx - cy);
             if (p.d_render) {
                 const size_t pix = (size_t)gy * p.W + gx;
                 mp[pix] = inv * (2.f * mu2 * (A2 - A1) - 2.f * mu1 * S * (B2 - B1));       // dS/dmu1
@@ -174,8 +218,10 @@ __global__ void __launch_bounds__(THREADS) ssim_fwd_kernel(const LossParams p)
 
 __global__ void __launch_bounds__(THREADS) ssim_bwd_kernel(const LossParams p)
 {
-    __shared__ __align__(16) float s_d[3][IN][PITCH];
-    __shared__ __align__(16) float s_g[3][IN][TX];
+    __shared__ __align__(16) f32x2 s_d01[IN][PITCH];         // (dS/dmu1, dS/dE[x^2]) pairs
+    __shared__ __align__(16) float s_d2[IN][PITCH];          // dS/dE[xy]
+    __shared__ __align__(16) f32x2 s_g01[IN][TX];
+    __shared__ __align__(16) float s_g2[IN][TX];
     __shared__ float2 s_red[THREADS / 32];
     const int tid = threadIdx.x;
     const int plane = blockIdx.z;
@@ -183,53 +229,77 @@ __global__ void __launch_bounds__(THREADS) ssim_bwd_kernel(const LossParams p)
     const size_t HW = (size_t)p.H * p.W;
     const float a = p.cam_m ? expf(p.cam_m[plane]) : 1.0f, b = p.cam_c ? p.cam_c[plane] : 0.0f;
     const float* __restrict__ mp = p.maps + (size_t)plane * 3 * HW;
-
-    for (int idx = tid; idx < IN * IN; idx += THREADS) {
-        const int r = idx / IN, c = idx - r * IN;
-        const int gy = y0 - RAD + r, gx = x0 - RAD + c;
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-            const size_t pix = (size_t)gy * p.W + gx;
-            d0 = __ldg(mp + pix); d1 = __ldg(mp + HW + pix); d2 = __ldg(mp + 2 * HW + pix);
-        }
-        s_d[0][r][c] = d0; s_d[1][r][c] = d1; s_d[2][r][c] = d2;
-    }
-    __syncthreads();
-
-    for (int s = tid; s < 3 * IN * (TX / 4); s += THREADS) {
-        const int q = s / (IN * (TX / 4)), rem = s - q * (IN * (TX / 4));
-        const int r = rem >> 3, c0 = (rem & 7) * 4;
-        float v[16];
-        #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float4 f = *reinterpret_cast<const float4*>(&s_d[q][r][c0 + 4 * k]);
-            v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
-        }
-        float h[4];
-        #pragma unroll
-        for (int o = 0; o < 4; o++) {
-            float acc = 0.f;
-            #pragma unroll
-            for (int k = 0; k < WIN; k++) acc = fmaf(p.win.w[k], v[o + k], acc);
-            h[o] = acc;
-        }
-        *reinterpret_cast<float4*>(&s_g[q][r][c0]) = make_float4(h[0], h[1], h[2], h[3]);
-    }
-    __syncthreads();
-
     const int tx = tid & 31, ty = tid >> 5;
-    float g[3][4];
-    #pragma unroll
-    for (int q = 0; q < 3; q++) {
-        float v[14];
+
+    for (int r = ty; r < IN; r += THREADS / 32) {
+        const int gy = y0 - RAD + r;
+        const bool row_in = gy >= 0 && gy < p.H;
         #pragma unroll
-        for (int i = 0; i < 14; i++) v[i] = s_g[q][ty * 4 + i][tx];
+        for (int cc = 0; cc < 2; cc++) {
+            const int c = tx + 32 * cc;
+            if (c < IN) {
+                const int gx = x0 - RAD + c;
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+                if (row_in && gx >= 0 && gx < p.W) {
+                    const size_t pix = (size_t)gy * p.W + gx;
+                    d0 = __ldg(mp + pix); d1 = __ldg(mp + HW + pix); d2 = __ldg(mp + 2 * HW + pix);
+                }
+                s_d01[r][c] = pk2(d0, d1); s_d2[r][c] = d2;
+            }
+        }
+    }
+    __syncthreads();
+
+    for (int s = tid; s < IN * (TX / 4); s += THREADS) {
+        const int r = s >> 3, c0 = (s & 7) * 4;
+        f32x2 v[14];
+        float u[16];
+        #pragma unroll
+        for (int q = 0; q < 7; q++) {
+            const ulonglong2 f = *reinterpret_cast<const ulonglong2*>(&s_d01[r][c0 + 2 * q]);
+            v[2 * q] = f.x; v[2 * q + 1] = f.y;
+        }
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 f = *reinterpret_cast<const float4*>(&s_d2[r][c0 + 4 * q]);
+            u[4 * q] = f.x; u[4 * q + 1] = f.y; u[4 * q + 2] = f.z; u[4 * q + 3] = f.w;
+        }
+        f32x2 h01[4];
+        float h2[4];
         #pragma unroll
         for (int o = 0; o < 4; o++) {
-            float acc = 0.f;
+            f32x2 a01 = 0ull;
+            float a2 = 0.f;
             #pragma unroll
-            for (int k = 0; k < WIN; k++) acc = fmaf(p.win.w[k], v[o + k], acc);
-            g[q][o] = acc;
+            for (int k = 0; k < WIN; k++) {
+                a01 = fma2(p.win.ww[k], v[o + k], a01);
+                a2 = fmaf(p.win.w[k], u[o + k], a2);
+            }
+            h01[o] = a01; h2[o] = a2;
+        }
+        *reinterpret_cast<ulonglong2*>(&s_g01[r][c0]) = make_ulonglong2(h01[0], h01[1]);
+        *reinterpret_cast<ulonglong2*>(&s_g01[r][c0 + 2]) = make_ulonglong2(h01[2], h01[3]);
+        *reinterpret_cast<float4*>(&s_g2[r][c0]) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+    }
+    __syncthreads();
+
+    float g[3][4];
+    {
+        f32x2 v[14];
+        float u[14];
+        #pragma unroll
+        for (int i = 0; i < 14; i++) { v[i] = s_g01[ty * 4 + i][tx]; u[i] = s_g2[ty * 4 + i][tx]; }
+        #pragma unroll
+        for (int o = 0; o < 4; o++) {
+            f32x2 acc = 0ull;
+            float a2 = 0.f;
+            #pragma unroll
+            for (int k = 0; k < WIN; k++) {
+                acc = fma2(p.win.ww[k], v[o + k], acc);
+                a2 = fmaf(p.win.w[k], u[o + k], a2);
+            }
+            upk2(acc, g[0][o], g[1][o]);
+            g[2][o] = a2;
         }
     }
 
@@ -350,7 +420,12 @@ extern "C" int t4d_image_loss(const T4dImageLoss* q, gs_stream_t stream)
     {
         float g[WIN], sum = 0.f;
         for (int i = 0; i < WIN; i++) { g[i] = (float)exp(-(double)((i - RAD) * (i - RAD)) / (2.0 * 1.5 * 1.5)); sum += g[i]; }
-        for (int i = 0; i < WIN; i++) p.win.w[i] = g[i] / sum;
+        for (int i = 0; i < WIN; i++) {
+            p.win.w[i] = g[i] / sum;
+            uint32_t bits;
+            memcpy(&bits, &p.win.w[i], 4);
+            p.win.ww[i] = ((unsigned long long)bits << 32) | bits;
+        }
     }
     const dim3 grid(p.nbx, p.nby, q->V * 3);
     ssim_fwd_kernel<<<grid, THREADS, 0, s>>>(p);
