@@ -21,6 +21,7 @@
  *       helpers.py:115-116, external.py:71-116), and loss.backward() down to dL/d(rendered image).
  *   t4d_adam_step ............. `optimizer.step()` of torch.optim.Adam(param_groups, lr=0.0, eps=1e-15)
  *       (train.py:272-297, 672) fused with the boolean-mask overwrites that follow it (train.py:676-700).
+ *   t4d_dense_attribute ....... `compute_vertex_attribute_by_weight_2` (helpers.py:237-253; train.py:498-508).
  *   f3d_render_colors[_host] .. `_render_colors_core` (face3d/mesh/cython/mesh_core.cpp:169-234)
  *       as bound by `render_colors_core` (face3d/mesh/cython/mesh_core_cython.pyx:64-77) and
  *       reached through face3d/mesh/render.py:52-86 from helpers.py:956.
@@ -222,9 +223,22 @@ typedef struct T4dAdamSegment {    /* one named parameter = one torch param grou
     int32_t row_width;              /* elements per row (3 for means3D / colours / scales, 4 rotations, 1 opacities) */
     int32_t step;                   /* 1-based step count of this parameter (state['step'] after increment)     */
     float   lr;                     /* the group's current learning rate (update_optimizer, helpers.py:801-804) */
+    int32_t* step_device;           /* NULL, or a DEVICE counter of completed steps: the launch then derives the bias
+                                       corrections from it and advances it (CUDA-graph replay safe); `step` is ignored */
+    const float* lr_device;         /* with step_device only: NULL, or a DEVICE float holding the learning rate (so an
+                                       update_optimizer() between replays needs no re-capture); `lr` is then ignored */
 } T4dAdamSegment;
 /* `segments` is a HOST array; betas/eps as in torch.optim.Adam (reference: 0.9, 0.999, 1e-15). */
 int t4d_adam_step(const T4dAdamSegment* segments, int32_t nseg, float beta1, float beta2, float eps, gs_stream_t stream);
+
+/* Dense Gaussian-mesh attribute interpolation: compute_vertex_attribute_by_weight_2
+ * (helpers.py:237-253, called per frame from update_dense_states, train.py:498-508).  dense_out[n_base + n_new, channels]:
+ * rows < n_base copy `attribute`; row n_base + i = sum_j weight[i][j] * attribute[quad_faces[vertex_father[i]][j]],
+ * evaluated in float64 in NumPy's order and rounded once to float32 (bit-identical to the reference + `.float()`).
+ * All pointers are device pointers; quad_faces [F,4] int32, vertex_father [n_new] int32, weight [n_new,4] float64. */
+int t4d_dense_attribute(const float* attribute, int32_t n_base, int32_t channels, const int32_t* quad_faces,
+                        const int32_t* vertex_father, const double* weight, int32_t n_new, float* dense_out,
+                        gs_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -235,3 +235,96 @@ def test_training_iteration_like_train_py_661_700():
     h_t, p_t = run(False, 3)
     np.testing.assert_allclose(h_f[:3], h_t, rtol=2e-4)
     assert float((p_t["rgb_colors"].detach()[~mask] - init[~mask]).abs().max()) > 0
+
+
+def test_dense_attribute_bit_exact():
+    """compute_vertex_attribute_by_weight_2 (helpers.py:237-253) on the device: bit-identical to the reference function's
+    output after the caller's `.cuda().float()` (golden), and to the oracle on a 1M-vertex densification."""
+    from oracle import dense_oracle
+    from topo4d_b200 import dense
+    g = np.load(os.path.join(G, "dense.npz"))
+    for n in ("small", "wide"):
+        var = {k: g[f"{n}_{k}"] for k in ("dense_quad_faces", "dense_vertex_father", "dense_vertex_weight", "dense_vertex")}
+        out = dense.compute_vertex_attribute_by_weight_2(var, torch.tensor(g[n + "_attr"], device=DEV))
+        assert out.dtype == torch.float32 and out.is_cuda
+        np.testing.assert_array_equal(out.cpu().numpy(), g[n + "_ref_cuda_float"])
+    rng = np.random.default_rng(11)
+    n_base, n_quads, per = 60000, 15000, 64
+    quads = rng.integers(0, n_base, (n_quads, 4))
+    u, v = rng.uniform(0, 1, n_quads * per), rng.uniform(0, 1, n_quads * per)
+    var = {"dense_quad_faces": quads, "dense_vertex_father": np.repeat(np.arange(n_quads, dtype=np.int32), per)[:, None],
+           "dense_vertex_weight": np.stack([(1 - u) * (1 - v), u * (1 - v), u * v, (1 - u) * v], 1),
+           "dense_vertex": np.zeros((n_base + n_quads * per, 3))}
+    attr = rng.normal(0, 1, (n_base, 3)).astype(np.float32)
+    out = dense.compute_vertex_attribute_by_weight_2(var, torch.tensor(attr, device=DEV))
+    np.testing.assert_array_equal(out.cpu().numpy(), dense_oracle.compute_vertex_attribute_by_weight_2(var, attr))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        dense.compute_vertex_attribute_by_weight_2(var, torch.tensor(attr))
+
+
+def test_cuda_graph_iteration_matches_eager():
+    """A whole iteration (render -> fused loss -> backward -> FusedAdam(capturable)) captured by topo4d_b200.graph.capture and
+    replayed k times leaves the parameters where k eager iterations leave them; an lr edit between replays is honoured
+    after sync_hyperparams() without re-capture; non-capturable Adam refuses to be captured."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings as Camera
+    from diff_gaussian_rasterization import GaussianRasterizer as Renderer
+    from topo4d_b200 import graph, synth
+    dev = torch.device(DEV)
+    sc = synth.random_scene(3000, seed=5)
+    cam = synth.front_camera(160, 128)
+    settings = Camera(image_height=128, image_width=160, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.zeros(3, device=dev),
+                      scale_modifier=1.0, viewmatrix=torch.tensor(cam.viewmatrix, device=dev).reshape(1, 4, 4),
+                      projmatrix=torch.tensor(cam.projmatrix, device=dev).reshape(1, 4, 4), sh_degree=0,
+                      campos=torch.tensor(cam.campos, device=dev), prefiltered=False, debug=False)
+    gt = torch.rand(3, 128, 160, device=dev)
+
+    def build(capturable):
+        params = {k: torch.nn.Parameter(torch.tensor(v, device=dev)) for k, v in sc.items()}
+        params["cam_m"] = torch.nn.Parameter(torch.zeros(1, 3, device=dev))
+        params["cam_c"] = torch.nn.Parameter(torch.zeros(1, 3, device=dev))
+        lrs = {"means3D": 1e-4, "colors_precomp": 0.01, "rotations": 0.001, "opacities": 0.0, "scales": 0.001, "cam_m": 1e-3, "cam_c": 1e-3}
+        opt = optim.FusedAdam([{"params": [v], "name": k, "lr": lrs[k]} for k, v in params.items()], lr=0.0, eps=1e-15,
+                              capturable=capturable)
+
+        def it():
+            rv = {"means3D": params["means3D"], "colors_precomp": params["colors_precomp"],
+                  "rotations": torch.nn.functional.normalize(params["rotations"]), "opacities": params["opacities"],
+                  "scales": params["scales"], "means2D": torch.zeros_like(params["means3D"], requires_grad=True) + 0}
+            im = Renderer(raster_settings=settings)(**rv)[0]
+            loss = losses.image_loss(im, gt, params["cam_m"][0], params["cam_c"][0])
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+        return params, opt, it
+
+    def set_lr(opt, name, lr):
+        for g in opt.param_groups:
+            if g["name"] == name:
+                g["lr"] = lr
+
+    p_e, opt_e, it_e = build(False)
+    for k in range(9):
+        if k == 6:
+            set_lr(opt_e, "colors_precomp", 0.05)
+        it_e()
+    p_g, opt_g, it_g = build(True)
+    step = graph.capture(it_g, warmup=3)                 # 3 eager iterations ...
+    for k in range(3, 9):                                # ... then 6 replays
+        if k == 6:
+            set_lr(opt_g, "colors_precomp", 0.05)
+            opt_g.sync_hyperparams()
+        step.replay()
+    step.check()
+    assert len(step.states) == 1 and step.replays == 6
+    assert int(opt_g.state[p_g["colors_precomp"]]["step"].item()) == 9
+    for k in p_e:
+        a, b = p_e[k].detach(), p_g[k].detach()
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5 * float(a.abs().max()) + 1e-7), k
+    assert float((p_e["colors_precomp"].detach() - torch.tensor(sc["colors_precomp"], device=dev)).abs().max()) > 1e-3
+    _, opt_n, it_n = build(False)
+    it_n()
+    with pytest.raises(RuntimeError, match="capturable"):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            it_n()

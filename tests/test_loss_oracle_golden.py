@@ -68,3 +68,13 @@ def test_adam_oracle_matches_torch_optim_adam_as_the_reference_builds_it():
             p, m, v = loss_oracle.adam_steps(g[k + "_init"], grads, lr)
         np.testing.assert_allclose(p, g[k + "_final"], rtol=2e-6, atol=2e-7)
         assert rel_err(m, g[k + "_exp_avg"]) < 5e-5 and rel_err(v, g[k + "_exp_avg_sq"]) < 5e-5      # golden is fp32
+
+
+def test_dense_attribute_oracle_is_bit_identical_to_the_reference_function():
+    from oracle import dense_oracle
+    g = np.load(os.path.join(G, "dense.npz"))
+    for n in ("small", "wide"):
+        var = {k: g[f"{n}_{k}"] for k in ("dense_quad_faces", "dense_vertex_father", "dense_vertex_weight", "dense_vertex")}
+        out = dense_oracle.compute_vertex_attribute_by_weight_2(var, g[n + "_attr"])
+        np.testing.assert_array_equal(out, g[n + "_ref_cuda_float"])
+        np.testing.assert_array_equal(out[:g[n + "_attr"].shape[0]], g[n + "_attr"])

@@ -58,7 +58,8 @@ T4D_ADAM_MAX_SEGMENTS = 24
 
 class T4dAdamSegment(C.Structure):
     _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("pin_mask", _vp), ("pin_values", _vp),
-                ("count", C.c_int64), ("row_width", C.c_int32), ("step", C.c_int32), ("lr", C.c_float)]
+                ("count", C.c_int64), ("row_width", C.c_int32), ("step", C.c_int32), ("lr", C.c_float), ("step_device", _vp),
+                ("lr_device", _vp)]
 
 
 # every symbol include/topo4d_b200.h declares: (name, restype, argtypes)
@@ -80,6 +81,7 @@ SYMBOLS = {
     "f3d_image_to_u8": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "t4d_image_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "t4d_image_loss": (C.c_int, [C.POINTER(T4dImageLoss), _vp]),
+    "t4d_dense_attribute": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp, _vp]),
     "t4d_adam_step": (C.c_int, [C.POINTER(T4dAdamSegment), C.c_int32, C.c_float, C.c_float, C.c_float, _vp]),
 }
 

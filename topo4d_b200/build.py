@@ -31,6 +31,7 @@ SOURCES = [
     ("f3d_render.cu", ["--fmad=false"]),
     ("t4d_loss.cu", []),
     ("t4d_optim.cu", []),
+    ("t4d_dense.cu", []),
 ]
 
 

@@ -23,6 +23,8 @@ KERNELS_PER_FORWARD, KERNELS_PER_BACKWARD = 6, 2
 
 # remembered instance capacity per problem shape (grown on overflow)
 _CAP_MEMO: dict[tuple, int] = {}
+_COUNT_MEMO: dict[tuple, int] = {}  # last measured (tile, Gaussian) instance count per problem shape
+_TOUCHED_KEYS: set = set()         # problem shapes rendered since the set was last cleared (graph.capture sizes headroom)
 # remembered number of non-empty tiles per problem shape: picks the blend kernels' pixels-per-thread variant
 _ACTIVE_MEMO: dict[tuple, int] = {}
 _WS_BYTES: dict[tuple, int] = {}
@@ -115,6 +117,7 @@ class RasterState:
             self._status = st
             if self.key:
                 _ACTIVE_MEMO[self.key] = int(st.num_active_tiles)
+                _COUNT_MEMO[self.key] = int(st.num_instances)
         if self._status is None:
             st = GsStatus()
             with torch.cuda.device(self.device):
@@ -125,6 +128,7 @@ class RasterState:
             self._status = st
             if self.key:
                 _ACTIVE_MEMO[self.key] = int(st.num_active_tiles)
+                _COUNT_MEMO[self.key] = int(st.num_instances)
         return self._status
 
     def view(self) -> dict:
@@ -200,6 +204,7 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
     out = GsForwardOut(_ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii))
 
     key = (N, V, H, W, dev.index)
+    _TOUCHED_KEYS.add(key)
     cap = int(cap_instances) if cap_instances is not None else _CAP_MEMO.get(key)
     px = int(blend_px) if blend_px else pick_blend_px(_ACTIVE_MEMO.get(key))
 
@@ -215,6 +220,9 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
         return pr, ws
 
     with torch.cuda.device(dev):
+        if cap is None and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("topo4d_b200: the first render of a new shape sizes its workspace with a synchronising counting "
+                               "pass and cannot be captured in a CUDA graph: run the step eagerly once before capturing")
         if cap is None:
             # first call for this shape: exact count from a preprocess-only pass
             pr, ws = make_problem(0)

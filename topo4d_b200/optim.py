@@ -20,11 +20,16 @@ from . import _lib
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         if lr < 0.0 or eps < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._pins: dict[int, tuple[torch.Tensor, torch.Tensor | None]] = {}
+        # capturable=True: step counters and learning rates live on the device, so a step() captured in a CUDA graph
+        # (topo4d_b200.graph.capture) advances correctly at every replay; after editing param_groups[i]['lr']
+        # (update_optimizer, helpers.py:801-804) call sync_hyperparams() -- no re-capture needed.
+        self.capturable = bool(capturable)
+        self._lr_dev: torch.Tensor | None = None
         g0 = self.param_groups[0]
         if any(g["betas"] != g0["betas"] or g["eps"] != g0["eps"] for g in self.param_groups):
             raise ValueError("FusedAdam shares betas / eps across groups (as the reference does); only lr is per group")
@@ -41,6 +46,12 @@ class FusedAdam(torch.optim.Optimizer):
         v = None if values is None else values.to(device=param.device, dtype=torch.float32).expand_as(param).contiguous()
         self._pins[id(param)] = (m, v)
 
+    def sync_hyperparams(self) -> None:
+        """Capturable mode: push the groups' current learning rates to their device slots (one small H2D copy)."""
+        if self._lr_dev is not None:
+            host = torch.tensor([float(g["lr"]) for g in self.param_groups], dtype=torch.float32)
+            self._lr_dev.copy_(host, non_blocking=False)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -49,7 +60,10 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         segs, keep = [], []
         dev = None
-        for g in self.param_groups:
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if capturing and not self.capturable:
+            raise RuntimeError("FusedAdam.step() inside CUDA-graph capture needs FusedAdam(..., capturable=True)")
+        for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
                 if p.grad is None:
                     continue
@@ -64,19 +78,34 @@ class FusedAdam(torch.optim.Optimizer):
                 grad = p.grad if (p.grad.is_contiguous() and p.grad.dtype is torch.float32) else p.grad.float().contiguous()
                 st = self.state[p]
                 if not st:
-                    st["step"] = 0
+                    if capturing:
+                        raise RuntimeError("run at least one eager step() before capturing (optimizer state is created lazily)")
+                    st["step"] = torch.zeros((), dtype=torch.int32, device=p.device) if self.capturable else 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["step"] = int(st["step"]) + 1
+                step_dev = lr_dev = None
+                if self.capturable:
+                    if self._lr_dev is None:
+                        if capturing:
+                            raise RuntimeError("run at least one eager step() before capturing")
+                        self._lr_dev = torch.zeros(len(self.param_groups), dtype=torch.float32, device=p.device)
+                    step_dev = st["step"].data_ptr()
+                    lr_dev = self._lr_dev.data_ptr() + 4 * gi
+                    step_host = 0
+                else:
+                    st["step"] = int(st["step"]) + 1
+                    step_host = st["step"]
                 pin = self._pins.get(id(p))
                 rw = int(p.numel() // p.shape[0]) if (pin is not None and p.dim() > 0 and p.shape[0] > 0) else 1
                 segs.append(_lib.T4dAdamSegment(p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                                                 None if pin is None else pin[0].data_ptr(),
                                                 None if pin is None or pin[1] is None else pin[1].data_ptr(),
-                                                p.numel(), rw, st["step"], float(g["lr"])))
+                                                p.numel(), rw, step_host, float(g["lr"]), step_dev, lr_dev))
                 keep.append(grad)
         if not segs:
             return loss
+        if self.capturable and not capturing:
+            self.sync_hyperparams()             # eager steps always see the current lrs
         b1, b2 = self.param_groups[0]["betas"]
         eps = self.param_groups[0]["eps"]
         L = _lib.lib()

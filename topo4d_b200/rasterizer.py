@@ -67,6 +67,9 @@ def pack_settings(rs: GaussianRasterizationSettings) -> torch.Tensor:
 # TOPO4D_B200_SYNC=0: fully asynchronous forward; the status of call k is checked at call k+1 (by then it is
 # long complete, so the check is free) and an overflow raises there after growing the capacity for the retry.
 _PENDING: list = []
+# Forwards issued while the current stream is being captured into a CUDA graph cannot touch the host at all: they run
+# with check="none" and their states are logged here so that topo4d_b200.graph.capture can verify them after replays.
+_CAPTURE_LOG: list = []
 
 
 def _sync_mode() -> bool:
@@ -90,14 +93,18 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 cameras, image_height, image_width, sh_degree, scale_modifier, debug):
-        sync = _sync_mode()
-        if not sync:
+        capturing = means3D.is_cuda and torch.cuda.is_current_stream_capturing()
+        sync = _sync_mode() and not capturing
+        if not sync and not capturing:
             _check_pending()
         color, radii, depth, alpha, state = engine.forward(
             means3D, opacities, cameras, image_height, image_width, shs=sh, colors_precomp=colors_precomp,
             scales=scales, rotations=rotations, cov3D_precomp=cov3Ds_precomp, sh_degree=sh_degree,
-            scale_modifier=scale_modifier, debug=debug, check="sync" if sync else "deferred")
-        if not sync:
+            scale_modifier=scale_modifier, debug=debug and not capturing,
+            check="sync" if sync else ("none" if capturing else "deferred"))
+        if capturing:
+            _CAPTURE_LOG.append(state)
+        elif not sync:
             _PENDING.append(state)
         ctx.state = state
         ctx.shapes = tuple(None if t is None else t.shape for t in
