@@ -95,6 +95,9 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host threads it can
+    if os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import gs_oracle
     scene, cams = workload(a)
     rng = np.random.default_rng(0)
@@ -215,13 +218,15 @@ def run_ours(a):
                       torch.full_like(alpha, 0.1 / (H * W))))
         del color, depth, alpha, st, target
     flat = None
+    flat_bufs = [None] * len(groups)      # gradient buffers are allocated once and reused (the all-reduce runs in place)
 
     def step(params, ev=None):
         nonlocal flat
         total = None
         for g in range(len(groups)):
             *_, st = fwd(g, params, ev)
-            gb = engine.backward(st, *gimgs[g], stage_events=ev)
+            gb = engine.backward(st, *gimgs[g], flat=flat_bufs[g], stage_events=ev)
+            flat_bufs[g] = gb.flat
             total = gb.flat if total is None else total.add_(gb.flat)
         flat = total
         if world > 1:
