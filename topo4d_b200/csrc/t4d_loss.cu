@@ -95,21 +95,46 @@ __global__ void __launch_bounds__(THREADS) ssim_fwd_kernel(const LossParams p)
     const float* __restrict__ tp = p.target + (size_t)plane * HW;
     const int tx = tid & 31, ty = tid >> 5;
 
-    // the convolution pads the AFFINE image with zeros (conv2d padding=5 on `im`): outside pixels are x = y = 0
-    for (int r = ty; r < IN; r += THREADS / 32) {
-        const int gy = y0 - RAD + r;
-        const bool row_in = gy >= 0 && gy < p.H;
-        #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const int c = tx + 32 * cc;
-            if (c < IN) {
-                const int gx = x0 - RAD + c;
-                float x = 0.f, y = 0.f;
-                if (row_in && gx >= 0 && gx < p.W) {
-                    x = fmaf(a, __ldg(rp + (size_t)gy * p.W + gx), b);
-                    y = __ldg(tp + (size_t)gy * p.W + gx);
+    // the convolution pads the AFFINE image with zeros (conv2d padding=5 on `im`): outside pixels are x = y = 0.
+    // All of a thread's global loads are issued before the first shared-memory store (one exposed latency, not six);
+    // tiles whose halo lies inside the image (9 of 10 at 1080p) take a path without per-element bounds tests.
+    {
+        constexpr int NR = (IN + THREADS / 32 - 1) / (THREADS / 32);      // 6 row slots per thread
+        float xr[NR][2], yr[NR][2];
+        const bool interior = x0 >= RAD && y0 >= RAD && x0 - RAD + IN <= p.W && y0 - RAD + IN <= p.H;   // CTA-uniform
+        const int base = (y0 - RAD + ty) * p.W + (x0 - RAD + tx);          // 32-bit offsets inside one plane
+        if (interior) {
+            #pragma unroll
+            for (int i = 0; i < NR; i++) {
+                #pragma unroll
+                for (int cc = 0; cc < 2; cc++) {
+                    const bool ok = (ty + (THREADS / 32) * i < IN) && (tx + 32 * cc < IN);
+                    const int off = base + (THREADS / 32) * i * p.W + 32 * cc;
+                    xr[i][cc] = ok ? fmaf(a, __ldg(rp + off), b) : 0.f;
+                    yr[i][cc] = ok ? __ldg(tp + off) : 0.f;
                 }
-                s_xy[r][c] = pk2(x, y);
+            }
+        } else {
+            #pragma unroll
+            for (int i = 0; i < NR; i++) {
+                const int r = ty + (THREADS / 32) * i, gy = y0 - RAD + r;
+                #pragma unroll
+                for (int cc = 0; cc < 2; cc++) {
+                    const int c = tx + 32 * cc, gx = x0 - RAD + c;
+                    const bool ok = r < IN && c < IN && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+                    const int off = base + (THREADS / 32) * i * p.W + 32 * cc;
+                    xr[i][cc] = ok ? fmaf(a, __ldg(rp + off), b) : 0.f;
+                    yr[i][cc] = ok ? __ldg(tp + off) : 0.f;
+                }
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < NR; i++) {
+            const int r = ty + (THREADS / 32) * i;
+            #pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const int c = tx + 32 * cc;
+                if (r < IN && c < IN) s_xy[r][c] = pk2(xr[i][cc], yr[i][cc]);
             }
         }
     }
@@ -195,7 +220,7 @@ __global__ void __launch_bounds__(THREADS) ssim_fwd_kernel(const LossParams p)
             const float s11 = m[2][o] - mu1_sq, s22 = m[3][o] - mu2_sq, s12 = m[4][o] - mu12;
             const float A1 = 2.f * mu12 + SSIM_C1, A2 = 2.f * s12 + SSIM_C2;
             const float B1 = mu1_sq + mu2_sq + SSIM_C1, B2 = s11 + s22 + SSIM_C2;
-            const float inv = 1.0f / (B1 * B2);
+            const float inv = __fdividef(1.0f, B1 * B2);      // rcp.approx: 1 ulp, far inside the 1e-5 budget
             const float S = (A1 * A2) * inv;
             ssim_sum += S;
             float cx, cy;
@@ -231,20 +256,33 @@ __global__ void __launch_bounds__(THREADS) ssim_bwd_kernel(const LossParams p)
     const float* __restrict__ mp = p.maps + (size_t)plane * 3 * HW;
     const int tx = tid & 31, ty = tid >> 5;
 
-    for (int r = ty; r < IN; r += THREADS / 32) {
-        const int gy = y0 - RAD + r;
-        const bool row_in = gy >= 0 && gy < p.H;
+    {
+        constexpr int NR = (IN + THREADS / 32 - 1) / (THREADS / 32);
+        float d[NR][2][3];
+        const bool interior = x0 >= RAD && y0 >= RAD && x0 - RAD + IN <= p.W && y0 - RAD + IN <= p.H;   // CTA-uniform
+        const int base = (y0 - RAD + ty) * p.W + (x0 - RAD + tx);
+        const float* __restrict__ m1 = mp + HW;
+        const float* __restrict__ m2 = mp + 2 * HW;
         #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const int c = tx + 32 * cc;
-            if (c < IN) {
-                const int gx = x0 - RAD + c;
-                float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-                if (row_in && gx >= 0 && gx < p.W) {
-                    const size_t pix = (size_t)gy * p.W + gx;
-                    d0 = __ldg(mp + pix); d1 = __ldg(mp + HW + pix); d2 = __ldg(mp + 2 * HW + pix);
-                }
-                s_d01[r][c] = pk2(d0, d1); s_d2[r][c] = d2;
+        for (int i = 0; i < NR; i++) {
+            const int r = ty + (THREADS / 32) * i, gy = y0 - RAD + r;
+            #pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const int c = tx + 32 * cc, gx = x0 - RAD + c;
+                const bool ok = r < IN && c < IN && (interior || (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W));
+                const int off = base + (THREADS / 32) * i * p.W + 32 * cc;
+                d[i][cc][0] = ok ? __ldg(mp + off) : 0.f;
+                d[i][cc][1] = ok ? __ldg(m1 + off) : 0.f;
+                d[i][cc][2] = ok ? __ldg(m2 + off) : 0.f;
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < NR; i++) {
+            const int r = ty + (THREADS / 32) * i;
+            #pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const int c = tx + 32 * cc;
+                if (r < IN && c < IN) { s_d01[r][c] = pk2(d[i][cc][0], d[i][cc][1]); s_d2[r][c] = d[i][cc][2]; }
             }
         }
     }

@@ -18,8 +18,9 @@ from ._lib import GS_CAM_FLOATS, GsBackwardIO, GsForwardOut, GsProblem, GsStatus
 FWD_STAGES = (("preprocess", _lib.GS_FWD_PREPROCESS), ("scatter", _lib.GS_FWD_SCATTER), ("sort_gather", _lib.GS_FWD_SORT),
               ("blend_fwd", _lib.GS_FWD_BLEND))
 BWD_STAGES = (("blend_bwd", _lib.GS_BWD_BLEND), ("preprocess_bwd", _lib.GS_BWD_PREPROCESS))
-# kernels launched by one forward / one backward call (memsets are not kernels)
-KERNELS_PER_FORWARD, KERNELS_PER_BACKWARD = 6, 2
+# kernels launched by one forward / one backward call (memsets are not kernels): preprocess, fused tile scan (two
+# launches only when V*tiles > 4096 * SM count), scatter, sort_gather, blend_fwd | blend_bwd, preprocess_bwd
+KERNELS_PER_FORWARD, KERNELS_PER_BACKWARD = 5, 2
 
 # remembered instance capacity per problem shape (grown on overflow)
 _CAP_MEMO: dict[tuple, int] = {}
