@@ -320,7 +320,7 @@ def run_ours(a):
         # measured DRAM traffic of the same kernel from the committed ncu capture (only valid for the same workload)
         traffic, traffic_src = None, None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01h_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01i_traffic.json")))
             w = tj["workload"]
             if (w["views_per_launch"], w["width"], w["height"], w["gaussians"], w["sh_degree"], w["opacity"]) == \
                     (vpl, a.width, a.height, a.gaussians, a.sh_degree, a.opacity):

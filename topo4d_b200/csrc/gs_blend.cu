@@ -7,9 +7,9 @@
 //
 //   * work = (view, 16x16 binning tile).  Persistent CTAs pull tiles from device-side queues (atomic counters in
 //     the status block): the compacted list of NON-EMPTY tiles, and -- forward only -- groups of 16 tiles whose
-//     empty members just receive the background.  Even CTAs start on the heavy queue, odd CTAs on the fill
-//     queue, so the issue-bound blending and the HBM-bound background stream overlap on every SM and nobody
-//     idles on a static tile->CTA map.
+//     empty members just receive the background.  One worker warp in eight starts on the fill queue, the others on
+//     the heavy queue (each falls over to the other queue when its own runs dry), so the issue-bound blending and the
+//     HBM-bound background stream overlap on every SM and nobody idles on a static tile->CTA map.
 //   * a thread owns a vertical comb of PX pixels (x, y+4k): lane (lx,ly) of a warp sits at column lx of the
 //     warp's 8 columns, rows ly+4k.  The column terms of the quadratic form are shared by the PX pixels (3 FP
 //     ops per pixel for `power`), and pixel slot k of a warp is one COMPACT 8x4 block, so the divergent blend
@@ -52,6 +52,11 @@ constexpr int WPC = GS_WPC;
 // Minimum resident CTAs per SM asked of ptxas: after the warp-level compaction the record loop is a dependent
 // ffs -> address -> LDS -> FMA chain, so the kernels want warps more than registers (measured at 64-thread CTAs:
 // bwd 12 -> 72 regs, fwd 14 -> 70 regs, no spills, 5-8 % faster than the unconstrained build).
+// One worker in GS_FILL_EVERY starts on the background-fill queue (the others start blending); a few warps are enough
+// to keep the HBM write stream busy, the rest hide the blend path's latency.
+#ifndef GS_FILL_EVERY
+#define GS_FILL_EVERY 8
+#endif
 #ifndef GS_BWD_MINB
 #define GS_BWD_MINB (24 / GS_WPC)
 #endif
@@ -215,7 +220,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
     const size_t HW = (size_t)p.H * p.W;
     const bool vec = (p.W & 3) == 0;
     const unsigned n_groups = (unsigned)((p.total_tiles + GS_FILL_GROUP - 1) / GS_FILL_GROUP);
-    const bool prefer_fill = (blockIdx.x * WPC + warp) & 1;
+    const bool prefer_fill = ((blockIdx.x * WPC + warp) % GS_FILL_EVERY) == GS_FILL_EVERY - 1;
 
     for (;;) {
         long long item = 0;
