@@ -95,3 +95,43 @@ def test_product_path_never_imports_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b|oracle/_|libgs_oracle|libf3d_(ref|oracle)", txt, flags=re.M):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_loop_tail_abi_validation_without_gpu():
+    """t4d_* entry points: struct layouts, workspace arithmetic and argument validation (no compute)."""
+    import torch
+    from topo4d_b200 import dense, losses, optim
+    L = _lib.lib()
+    # LP64 layouts of the header structs: 3 int32 + 2 float (20, padded to 24) + 8 pointers + pointer + size_t
+    assert C.sizeof(_lib.T4dImageLoss) == 24 + 8 * 8 + 8 + 8
+    # 6 pointers + int64 + 2 int32 + float (+4 pad) + 2 pointers
+    assert C.sizeof(_lib.T4dAdamSegment) == 6 * 8 + 8 + 4 + 4 + 8 + 2 * 8
+    nblk = ((1920 + 31) // 32) * ((1080 + 31) // 32)
+    ws = L.t4d_image_loss_workspace_bytes(2, 1080, 1920)
+    assert ws >= 2 * 9 * 1080 * 1920 * 4 + 2 * 2 * 3 * nblk * 8 and ws < 2 * 9 * 1080 * 1920 * 4 + 2 * 2 * 3 * nblk * 8 + 3 * 256
+    assert L.t4d_image_loss_workspace_bytes(0, 8, 8) == 0
+    assert L.t4d_image_loss(None, None) == _lib.GS_E_BAD_ARGS
+    bad = _lib.T4dImageLoss(V=1, H=8, W=8, w_l1=0.8, w_ssim=0.2)                      # no pointers
+    assert L.t4d_image_loss(C.byref(bad), None) == _lib.GS_E_BAD_ARGS
+    assert L.t4d_adam_step(None, 1, 0.9, 0.999, 1e-15, None) == _lib.GS_E_BAD_ARGS
+    seg = (_lib.T4dAdamSegment * 1)(_lib.T4dAdamSegment(count=16, row_width=1, step=0, lr=0.1))      # step 0 / NULL tensors
+    assert L.t4d_adam_step(seg, 1, 0.9, 0.999, 1e-15, None) == _lib.GS_E_BAD_ARGS
+    assert L.t4d_adam_step(seg, _lib.T4D_ADAM_MAX_SEGMENTS + 1, 0.9, 0.999, 1e-15, None) == _lib.GS_E_BAD_ARGS
+    assert L.t4d_dense_attribute(None, 4, 3, None, None, None, 2, None, None) == _lib.GS_E_BAD_ARGS
+    assert L.t4d_dense_attribute(None, 0, 3, None, None, None, 0, None, None) == 0      # nothing to do
+    # the host mirrors refuse CPU tensors: there is no CPU fallback on the product path
+    x = torch.rand(3, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        losses.image_loss(x, x)
+    with pytest.raises(ValueError):
+        losses.image_loss(x, x, torch.zeros(3), None)
+    with pytest.raises(NotImplementedError):
+        losses.calc_ssim(x, x, window_size=7)
+    p = torch.nn.Parameter(torch.zeros(4, 3))
+    p.grad = torch.ones(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        optim.FusedAdam([{"params": [p], "name": "means3D", "lr": 0.1}], lr=0.0, eps=1e-15).step()
+    with pytest.raises(ValueError):
+        optim.FusedAdam([{"params": [p], "lr": 0.1, "eps": 1e-8}, {"params": [torch.nn.Parameter(torch.zeros(2))], "lr": 0.1, "eps": 1e-3}])
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        dense.compute_vertex_attribute_by_weight_2({}, torch.zeros(4, 3))
