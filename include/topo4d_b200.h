@@ -21,6 +21,7 @@
  *       helpers.py:115-116, external.py:71-116), and loss.backward() down to dL/d(rendered image).
  *   t4d_adam_step ............. `optimizer.step()` of torch.optim.Adam(param_groups, lr=0.0, eps=1e-15)
  *       (train.py:272-297, 672) fused with the boolean-mask overwrites that follow it (train.py:676-700).
+ *   t4d_activate[_backward] ... the activations of `params2rendervar` (helpers.py:91-112) and their autograd backward.
  *   t4d_dense_attribute ....... `compute_vertex_attribute_by_weight_2` (helpers.py:237-253; train.py:498-508).
  *   f3d_render_colors[_host] .. `_render_colors_core` (face3d/mesh/cython/mesh_core.cpp:169-234)
  *       as bound by `render_colors_core` (face3d/mesh/cython/mesh_core_cython.pyx:64-77) and
@@ -230,6 +231,16 @@ typedef struct T4dAdamSegment {    /* one named parameter = one torch param grou
 } T4dAdamSegment;
 /* `segments` is a HOST array; betas/eps as in torch.optim.Adam (reference: 0.9, 0.999, 1e-15). */
 int t4d_adam_step(const T4dAdamSegment* segments, int32_t nseg, float beta1, float beta2, float eps, gs_stream_t stream);
+
+/* Fused parameter activations of params2rendervar (helpers.py:91-112): rotations = normalize(unnorm_rotations) [N,4]
+ * (x / max(||x||, 1e-12), as torch.nn.functional.normalize), opacities = sigmoid(logit_opacities) [N,1],
+ * scales = exp(log_scales) [N,3]; and their backward.  Gradient inputs / outputs of the backward may be NULL
+ * (NULL input = zero gradient, NULL output = not wanted).  Quaternion arrays must be 16-byte aligned. */
+int t4d_activate(const float* unnorm_rotations, const float* logit_opacities, const float* log_scales, int32_t N,
+                 float* rotations, float* opacities, float* scales, gs_stream_t stream);
+int t4d_activate_backward(const float* unnorm_rotations, const float* opacities, const float* scales,
+                          const float* dL_drotations, const float* dL_dopacities, const float* dL_dscales, int32_t N,
+                          float* dL_dunnorm_rotations, float* dL_dlogit_opacities, float* dL_dlog_scales, gs_stream_t stream);
 
 /* Dense Gaussian-mesh attribute interpolation: compute_vertex_attribute_by_weight_2
  * (helpers.py:237-253, called per frame from update_dense_states, train.py:498-508).  dense_out[n_base + n_new, channels]:

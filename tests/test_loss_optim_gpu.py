@@ -348,3 +348,65 @@ def test_synthetic_training_loop_tracks_the_sequence(tmp_path):
     assert f1["loss_last"] < f1["loss_first"], f1
     assert f0["pinned_rows_max_dev"] == 0.0 and f1["pinned_rows_max_dev"] == 0.0
     assert 0.0 < f0["bake_mean_u8"] < 255.0
+
+
+def test_fused_params2rendervar_matches_the_reference_expression():
+    """helpers.py:91-112: normalize / sigmoid / exp outside the op.  Values and gradients of the fused op against the
+    reference's own PyTorch expression on the same device (fp32; tolerance 2e-6 relative), incl. a zero quaternion (the
+    eps-clamped branch of F.normalize) and the means2D contract (a leaf whose .grad the rasterizer fills)."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings as Camera
+    from diff_gaussian_rasterization import GaussianRasterizer as Renderer
+    from topo4d_b200 import activations, synth
+    torch.manual_seed(3)
+    n = 5000
+    dev = torch.device(DEV)
+    base = {"means3D": torch.randn(n, 3, device=dev) * 0.3, "rgb_colors": torch.rand(n, 3, device=dev),
+            "unnorm_rotations": torch.randn(n, 4, device=dev) * 3.0, "logit_opacities": torch.randn(n, 1, device=dev) * 4.0,
+            "log_scales": torch.randn(n, 3, device=dev) - 3.5}
+    base["unnorm_rotations"][7] = 0.0
+    w = {k: torch.randn_like(base[k]) for k in ("unnorm_rotations", "logit_opacities", "log_scales")}
+
+    def run(fused):
+        p = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        if fused:
+            rv = activations.params2rendervar(p)
+        else:
+            rv = {"means3D": p["means3D"], "colors_precomp": p["rgb_colors"],
+                  "rotations": torch.nn.functional.normalize(p["unnorm_rotations"]), "opacities": torch.sigmoid(p["logit_opacities"]),
+                  "scales": torch.exp(p["log_scales"]), "means2D": torch.zeros_like(p["means3D"], requires_grad=True) + 0}
+        total = (rv["rotations"] * w["unnorm_rotations"]).sum() + (rv["opacities"] * w["logit_opacities"]).sum()
+        (total + (rv["scales"] * w["log_scales"]).sum()).backward()
+        return rv, p
+    rf, pf = run(True)
+    rt, pt = run(False)
+    assert set(rf) == set(rt)
+    for k in ("rotations", "opacities", "scales"):
+        assert rf[k].shape == rt[k].shape
+        assert torch.allclose(rf[k], rt[k], rtol=2e-6, atol=1e-7), k
+    for k in ("unnorm_rotations", "logit_opacities", "log_scales"):
+        assert torch.allclose(pf[k].grad, pt[k].grad, rtol=2e-5, atol=1e-6 * float(pt[k].grad.abs().max())), k
+    # through the rasterizer: same image, means2D.grad retained exactly as the reference reads it (train.py:304,311)
+    cam = synth.front_camera(128, 96)
+    settings = Camera(image_height=96, image_width=128, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.zeros(3, device=dev),
+                      scale_modifier=1.0, viewmatrix=torch.tensor(cam.viewmatrix, device=dev).reshape(1, 4, 4),
+                      projmatrix=torch.tensor(cam.projmatrix, device=dev).reshape(1, 4, 4), sh_degree=0,
+                      campos=torch.tensor(cam.campos, device=dev), prefiltered=False, debug=False)
+    outs = []
+    for fused in (True, False):
+        p = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        p["means3D"] = (base["means3D"] + torch.tensor([0.0, 0.0, 3.0], device=dev)).requires_grad_(True)
+        rv = activations.params2rendervar(p) if fused else {
+            "means3D": p["means3D"], "colors_precomp": p["rgb_colors"], "rotations": torch.nn.functional.normalize(p["unnorm_rotations"]),
+            "opacities": torch.sigmoid(p["logit_opacities"]), "scales": torch.exp(p["log_scales"]),
+            "means2D": torch.zeros_like(p["means3D"], requires_grad=True) + 0}
+        rv["means2D"].retain_grad()
+        im = Renderer(raster_settings=settings)(**rv)[0]
+        im.square().sum().backward()
+        outs.append((im.detach(), rv["means2D"].grad, p["log_scales"].grad))
+    # (a 1-ulp difference between expf here and torch.exp may flip a radius / alpha-threshold decision of single splats,
+    # so the renders are compared in norm, not element-wise)
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))      # noqa: E731
+    assert rel(outs[0][0], outs[1][0]) < 1e-3
+    assert outs[0][1] is not None and outs[0][1].shape == outs[1][1].shape and rel(outs[0][1], outs[1][1]) < 1e-2
+    assert float(outs[0][1][:, 2].abs().max()) == 0.0
+    assert rel(outs[0][2], outs[1][2]) < 1e-2

@@ -29,8 +29,11 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diff_gaussian_rasterization import GaussianRasterizationSettings as Camera  # noqa: E402
 from diff_gaussian_rasterization import GaussianRasterizer as Renderer  # noqa: E402
-from topo4d_b200 import graph, losses, optim, synth  # noqa: E402
+from topo4d_b200 import activations, graph, losses, optim, synth  # noqa: E402
 from topo4d_b200.face3d_compat import render as f3d  # noqa: E402
+
+
+FUSED_ACTIVATIONS = True
 
 
 def inverse_sigmoid(x):
@@ -68,6 +71,8 @@ def initialize_optimizer(params, lrs, capturable=False):
 
 
 def params2rendervar(params):
+    if FUSED_ACTIVATIONS:
+        return activations.params2rendervar(params)          # same dictionary, one launch each way
     return {"means3D": params["means3D"], "colors_precomp": params["rgb_colors"],
             "rotations": torch.nn.functional.normalize(params["unnorm_rotations"]),
             "opacities": torch.sigmoid(params["logit_opacities"]), "scales": torch.exp(params["log_scales"]),
@@ -109,8 +114,11 @@ def main():
     ap.add_argument("--gaussians", type=int, default=8280)
     ap.add_argument("--bake", type=int, default=1024, help="texture size of the per-frame face3d bake (0 = off)")
     ap.add_argument("--graph", action="store_true", help="one CUDA graph per camera for the whole iteration (single rank only)")
+    ap.add_argument("--torch-activations", action="store_true", help="helpers.py:91-112 as PyTorch ops instead of the fused kernel")
     ap.add_argument("--json", default="")
     a = ap.parse_args()
+    global FUSED_ACTIVATIONS
+    FUSED_ACTIVATIONS = not a.torch_activations
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -82,6 +82,8 @@ SYMBOLS = {
     "t4d_image_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "t4d_image_loss": (C.c_int, [C.POINTER(T4dImageLoss), _vp]),
     "t4d_dense_attribute": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp, _vp]),
+    "t4d_activate": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp]),
+    "t4d_activate_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp]),
     "t4d_adam_step": (C.c_int, [C.POINTER(T4dAdamSegment), C.c_int32, C.c_float, C.c_float, C.c_float, _vp]),
 }
 

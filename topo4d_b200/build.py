@@ -32,6 +32,7 @@ SOURCES = [
     ("t4d_loss.cu", []),
     ("t4d_optim.cu", []),
     ("t4d_dense.cu", []),
+    ("t4d_activate.cu", []),
 ]
 
 
