@@ -16,7 +16,7 @@ import torch  # noqa: E402
 
 from diff_gaussian_rasterization import GaussianRasterizationSettings as Camera  # noqa: E402
 from diff_gaussian_rasterization import GaussianRasterizer as Renderer  # noqa: E402
-from topo4d_b200 import activations, graph, losses, optim, synth  # noqa: E402
+from topo4d_b200 import graph, losses, optim, synth  # noqa: E402
 
 N, W, H, NCAM = 8280, 512, 375, 24
 LRS = {"means3D": 0.000016, "colors_precomp": 0.0025, "rotations": 0.001, "opacities": 0.0, "scales": 0.001, "cam_m": 1e-4, "cam_c": 1e-4}

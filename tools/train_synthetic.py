@@ -17,7 +17,6 @@ rank; G = 1 is the reference's one-view-per-step loop.
 """
 import argparse
 import json
-import math
 import os
 import sys
 import time
