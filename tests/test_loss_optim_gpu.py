@@ -410,3 +410,11 @@ def test_fused_params2rendervar_matches_the_reference_expression():
     assert outs[0][1] is not None and outs[0][1].shape == outs[1][1].shape and rel(outs[0][1], outs[1][1]) < 1e-2
     assert float(outs[0][1][:, 2].abs().max()) == 0.0
     assert rel(outs[0][2], outs[1][2]) < 1e-2
+
+
+def test_fused_params2rendervar_matches_reference_golden():
+    """The fused activations against the outputs and gradients of the reference's own params2rendervar (helpers.py:91-100),
+    incl. the zero quaternion (F.normalize's eps branch: gradient g * 1e12) and sigmoid(1000) = 1."""
+    from tests import activations_check
+    from topo4d_b200 import activations
+    activations_check.run_and_check(activations.params2rendervar, DEV)

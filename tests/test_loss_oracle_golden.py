@@ -78,3 +78,23 @@ def test_dense_attribute_oracle_is_bit_identical_to_the_reference_function():
         out = dense_oracle.compute_vertex_attribute_by_weight_2(var, g[n + "_attr"])
         np.testing.assert_array_equal(out, g[n + "_ref_cuda_float"])
         np.testing.assert_array_equal(out[:g[n + "_attr"].shape[0]], g[n + "_attr"])
+
+
+def test_activations_golden_is_reproduced_by_the_reference_expression():
+    """helpers.py:91-100 restated as plain PyTorch reproduces the fixture the reference function itself generated (this
+    also exercises the shared checker the GPU test applies to the fused kernel)."""
+    import torch
+    from tests import activations_check
+
+    def params2rendervar(params):
+        return {"means3D": params["means3D"], "colors_precomp": params["rgb_colors"],
+                "rotations": torch.nn.functional.normalize(params["unnorm_rotations"]),
+                "opacities": torch.sigmoid(params["logit_opacities"]), "scales": torch.exp(params["log_scales"]),
+                "means2D": torch.zeros_like(params["means3D"], requires_grad=True) + 0}
+    activations_check.run_and_check(params2rendervar, "cpu")
+    # a zero LEAF for means2D (what the fused mirror returns) satisfies the same contract
+    def with_leaf(params):
+        rv = params2rendervar(params)
+        rv["means2D"] = torch.zeros_like(params["means3D"], requires_grad=True)
+        return rv
+    activations_check.run_and_check(with_leaf, "cpu")
