@@ -202,7 +202,8 @@ def run_ours(a):
 
     # size capacities once (synchronising) and build the fixed dL/dpixel images of
     # L = L1(color, target) + 0.1 mean(depth) + 0.1 mean(alpha)  (SSIM excluded)
-    caps, gimgs, stats = [None] * len(groups), [], {"num_rendered": 0, "max_tile": 0}
+    caps, gimgs, stats = [None] * len(groups), [], {"num_rendered": 0, "max_tile": 0, "active_tiles": 0, "n_contrib_sum": 0,
+                                                    "covered_pixels": 0}
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     for g in range(len(groups)):
         color, radii, depth, alpha, st = engine.forward(t["means3D"], t["opacities"], cam_groups[g], H, W, shs=t.get("shs"),
@@ -212,6 +213,14 @@ def run_ours(a):
         caps[g] = int(s.num_instances * 1.1) + 4096
         stats["num_rendered"] += int(s.num_instances)
         stats["max_tile"] = max(stats["max_tile"], int(s.max_tile_instances))
+        try:        # workload statistics SURVEY 8(d) asks for (untimed, sizing pass only); never allowed to break the bench
+            stats["active_tiles"] += int(s.num_active_tiles)
+            nc = st.view()["n_contrib"]
+            stats["n_contrib_sum"] += int(nc.sum(dtype=torch.int64).item())
+            stats["covered_pixels"] += int((nc > 0).sum().item())
+            del nc
+        except Exception:  # noqa: BLE001
+            stats["active_tiles"] = stats["n_contrib_sum"] = stats["covered_pixels"] = None
         target = torch.rand(color.shape, device=dev, generator=gen)
         nv = len(groups[g])
         gimgs.append((torch.sign(color - target) / (3 * H * W), torch.full_like(depth, 0.1 / (H * W)),
@@ -342,7 +351,13 @@ def run_ours(a):
                 "dtype": "f32", "data": "synthetic",
                 "config": config_dict(a, {"views_per_rank": len(my_views), "views_per_launch": vpl,
                                           "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of the flat fp32 gradient buffer per step",
-                                          "num_rendered_rank0": stats["num_rendered"], "max_tile_instances": stats["max_tile"]}),
+                                          "num_rendered_rank0": stats["num_rendered"], "max_tile_instances": stats["max_tile"],
+                                          "non_empty_tiles_rank0": stats["active_tiles"],
+                                          "mean_tile_instances": (stats["num_rendered"] / stats["active_tiles"]) if stats["active_tiles"] else None,
+                                          "covered_pixel_fraction_rank0": (stats["covered_pixels"] / (len(my_views) * H * W))
+                                          if stats["covered_pixels"] is not None else None,
+                                          "mean_n_contrib_covered_pixels": (stats["n_contrib_sum"] / stats["covered_pixels"])
+                                          if stats["covered_pixels"] else None}),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof}
         if world == 1 and not a.no_cpu_baseline:
             nv = max(1, min(a.cpu_sample_views, a.views))
