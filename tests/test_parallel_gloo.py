@@ -69,3 +69,38 @@ def test_two_rank_view_parallel_matches_single_process(tmp_path):
     assert np.array_equal(r0, r1)                      # every rank ends with the same reduced buffer
     assert np.abs(ref).max() > 0
     np.testing.assert_allclose(r0, ref, rtol=1e-5, atol=1e-6 * np.abs(ref).max())
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    params = {"means3D": torch.nn.Parameter(torch.zeros(50, 3)), "unnorm_rotations": torch.nn.Parameter(torch.zeros(50, 4)),
+              "frozen": torch.nn.Parameter(torch.zeros(7)), "cam_m": torch.nn.Parameter(torch.zeros(24, 3))}
+    for k, p in params.items():
+        if k != "frozen":                              # no gradient on any rank: skipped, buffers still line up
+            p.grad = torch.randn(p.shape, generator=g)
+    parallel.allreduce_param_grads_(params, average=True)
+    np.savez(os.path.join(out_dir, f"g{rank}.npz"), **{k: p.grad.numpy() for k, p in params.items() if p.grad is not None})
+    dist.destroy_process_group()
+
+
+def test_two_rank_parameter_gradient_exchange(tmp_path):
+    """The training loop's exchange (tools/train_synthetic.py): every rank ends with the MEAN of the ranks' gradients,
+    parameter by parameter, from one flat all-reduce; without a process group it is the identity."""
+    port = _free_port()
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "g0.npz"), np.load(tmp_path / "g1.npz")
+    assert sorted(a.files) == ["cam_m", "means3D", "unnorm_rotations"]
+    for k in a.files:
+        np.testing.assert_array_equal(a[k], b[k])          # every rank ends with the same gradients
+    # regenerate what each rank drew (same generator protocol as the worker) and compare with the mean
+    draws = []
+    for rank in range(2):
+        g = torch.Generator().manual_seed(100 + rank)
+        draws.append({k: torch.randn(s, generator=g).numpy() for k, s in (("means3D", (50, 3)), ("unnorm_rotations", (50, 4)), ("cam_m", (24, 3)))})
+    for k in a.files:
+        np.testing.assert_allclose(a[k], 0.5 * (draws[0][k] + draws[1][k]), rtol=1e-6, atol=1e-7)
+    p = {"x": torch.nn.Parameter(torch.zeros(3))}
+    p["x"].grad = torch.ones(3)
+    assert parallel.allreduce_param_grads_(p)["x"].grad.equal(torch.ones(3))

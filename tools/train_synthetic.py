@@ -28,7 +28,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diff_gaussian_rasterization import GaussianRasterizationSettings as Camera  # noqa: E402
 from diff_gaussian_rasterization import GaussianRasterizer as Renderer  # noqa: E402
-from topo4d_b200 import activations, graph, losses, optim, synth  # noqa: E402
+from topo4d_b200 import activations, graph, losses, optim, parallel, synth  # noqa: E402
 from topo4d_b200.face3d_compat import render as f3d  # noqa: E402
 
 
@@ -155,7 +155,6 @@ def main():
     uv_v, uv_t, _ = synth.uv_grid_mesh(grid=64, res=max(a.bake, 64), seed=0, extras=False) if a.bake else (None, None, None)
 
     gen = torch.Generator().manual_seed(0)                   # the same view order on every rank
-    flat_names = list(params.keys())
     report = {"world": world, "frames": [], "config": vars(a)}
     t_start = time.perf_counter()
     steps_total = 0
@@ -189,15 +188,7 @@ def main():
                 continue
             loss = get_loss(params, cams[cam_id], cam_id, gts[cam_id])
             loss.backward()
-            if world > 1:                                    # ONE all-reduce of the flat gradient buffer per step
-                flat = torch.cat([params[k].grad.reshape(-1) for k in flat_names])
-                dist.all_reduce(flat)
-                flat.div_(world)
-                o = 0
-                for k in flat_names:
-                    n = params[k].numel()
-                    params[k].grad.copy_(flat[o:o + n].view_as(params[k]))
-                    o += n
+            parallel.allreduce_param_grads_(params, average=True)    # ONE all-reduce of a flat buffer per step (no-op at 1 rank)
             optimizer.step()
             optimizer.zero_grad(set_to_none=True)
             if i == 0:

@@ -25,3 +25,23 @@ def allreduce_flat_(flat: torch.Tensor, average: bool = False) -> torch.Tensor:
     if average:
         flat.div_(dist.get_world_size())
     return flat
+
+
+def allreduce_param_grads_(params, average: bool = True):
+    """The exchange of a view-parallel optimiser step for a parameter DICTIONARY (the reference keeps its parameters in
+    one, train.py:120-160): every ``.grad`` is packed into one flat fp32 buffer in the dictionary's order, reduced with
+    ONE collective (mean by default, so the step size does not depend on the number of ranks) and scattered back in
+    place.  Parameters without a gradient are skipped -- identically on every rank, or the buffers would not line up."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return params
+    names = [k for k, p in params.items() if p.grad is not None]
+    if not names:
+        return params
+    flat = torch.cat([params[k].grad.reshape(-1).float() for k in names])
+    allreduce_flat_(flat, average=average)
+    o = 0
+    for k in names:
+        g = params[k].grad
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+    return params
