@@ -1,8 +1,9 @@
 """Reference regime through the drop-in modules: one view per Adam step, 8 280 mesh-bound Gaussians, 512x375,
 colors_precomp, opacity 1 (train.py:138-146, 661-673, 771) -- what `train.py`'s geometry loop does 7000x per frame.
 Wall-clock per WHOLE iteration (render -> image loss -> backward -> optimiser step) in four configurations:
-  torch_tail   our rasterizer + the reference's own PyTorch loss expression (train.py:310,317) + torch.optim.Adam
-  fused_tail   our rasterizer + fused image loss (t4d_image_loss) + FusedAdam, eager
+  torch_tail   our rasterizer + the reference's own PyTorch activations (helpers.py:91-112), loss expression
+               (train.py:310,317) and torch.optim.Adam
+  fused_tail   our rasterizer + fused activations, fused image loss (t4d_image_loss) and FusedAdam, eager
   graph        the same, one CUDA graph per camera (topo4d_b200.graph.capture), replayed
   raster_only  render + L1 + backward only (no SSIM / optimiser): the number earlier rounds reported
     python tools/bench_dropin.py [iters=300] [--json out.json]"""
@@ -16,16 +17,25 @@ import torch  # noqa: E402
 
 from diff_gaussian_rasterization import GaussianRasterizationSettings as Camera  # noqa: E402
 from diff_gaussian_rasterization import GaussianRasterizer as Renderer  # noqa: E402
-from topo4d_b200 import graph, losses, optim, synth  # noqa: E402
+from topo4d_b200 import activations, graph, losses, optim, synth  # noqa: E402
 
 N, W, H, NCAM = 8280, 512, 375, 24
-LRS = {"means3D": 0.000016, "colors_precomp": 0.0025, "rotations": 0.001, "opacities": 0.0, "scales": 0.001, "cam_m": 1e-4, "cam_c": 1e-4}
+# the reference's parametrisation and learning rates (train.py:120-160, 272-297): raw log-scales / logits / unnormalised
+# quaternions, activated by params2rendervar (helpers.py:91-112) on every iteration.  (The r01h numbers in profiles/ were
+# taken with an earlier version of this tool that applied these learning rates to ACTIVATED scales, which made the splats
+# inflate during the run and the iterations heavier.)
+LRS = {"means3D": 0.000016, "rgb_colors": 0.0025, "unnorm_rotations": 0.001, "logit_opacities": 0.0, "log_scales": 0.001,
+       "cam_m": 1e-4, "cam_c": 1e-4}
 
 
 def make_state(dev):
     sc = synth.head_scene(N, seed=0, sh_degree=None, opacity="topo4d")
     cams = synth.ring_cameras(NCAM, w=W, h=H, radius=0.6, focal_over_h=1.6)
-    params = {k: torch.nn.Parameter(torch.tensor(v, device=dev)) for k, v in sc.items()}
+    t = {k: torch.tensor(v, device=dev) for k, v in sc.items()}
+    raw = {"means3D": t["means3D"], "rgb_colors": t["colors_precomp"], "unnorm_rotations": t["rotations"],
+           "logit_opacities": torch.log(torch.full_like(t["opacities"], 0.9999) / (1 - 0.9999)),       # train.py:142
+           "log_scales": torch.log(t["scales"])}
+    params = {k: torch.nn.Parameter(v.float().contiguous()) for k, v in raw.items()}
     params["cam_m"] = torch.nn.Parameter(torch.zeros(NCAM, 3, device=dev))
     params["cam_c"] = torch.nn.Parameter(torch.zeros(NCAM, 3, device=dev))
     settings = []
@@ -39,10 +49,14 @@ def make_state(dev):
     return params, settings, gts
 
 
-def render(params, cam):
-    rendervar = {"means3D": params["means3D"], "colors_precomp": params["colors_precomp"],
-                 "rotations": torch.nn.functional.normalize(params["rotations"]), "opacities": params["opacities"],
-                 "scales": params["scales"], "means2D": torch.zeros_like(params["means3D"], requires_grad=True) + 0}
+def render(params, cam, fused=False):
+    if fused:
+        rendervar = activations.params2rendervar(params)
+    else:                                                    # helpers.py:91-100 as the reference writes it
+        rendervar = {"means3D": params["means3D"], "colors_precomp": params["rgb_colors"],
+                     "rotations": torch.nn.functional.normalize(params["unnorm_rotations"]),
+                     "opacities": torch.sigmoid(params["logit_opacities"]), "scales": torch.exp(params["log_scales"]),
+                     "means2D": torch.zeros_like(params["means3D"], requires_grad=True) + 0}
     return Renderer(raster_settings=cam)(**rendervar)[0]
 
 
@@ -102,7 +116,7 @@ def main():
 
     def fused_tail(i):
         k = i % NCAM
-        im = render(params, settings[k])
+        im = render(params, settings[k], fused=True)
         losses.image_loss(im, gts[k], params["cam_m"][k], params["cam_c"][k]).backward()
         opt_f.step()
         opt_f.zero_grad(set_to_none=True)
@@ -113,7 +127,7 @@ def main():
 
     def make_iter(k):
         def it():
-            im = render(params, settings[k])
+            im = render(params, settings[k], fused=True)
             loss = losses.image_loss(im, gts[k], params["cam_m"][k], params["cam_c"][k])
             loss.backward()
             opt_g.step()
