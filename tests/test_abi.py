@@ -135,3 +135,27 @@ def test_loop_tail_abi_validation_without_gpu():
         optim.FusedAdam([{"params": [p], "lr": 0.1, "eps": 1e-8}, {"params": [torch.nn.Parameter(torch.zeros(2))], "lr": 0.1, "eps": 1e-3}])
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         dense.compute_vertex_attribute_by_weight_2({}, torch.zeros(4, 3))
+
+
+def test_debug_mode_leaves_a_snapshot_when_the_forward_fails(tmp_path, monkeypatch):
+    """settings.debug=True: like upstream's wrapper, a failing forward writes its inputs to snapshot_fw.dump before the
+    exception propagates (here the failure is the CUDA-only check on CPU tensors); debug=False writes nothing."""
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    monkeypatch.chdir(tmp_path)
+    cam = synth.front_camera(32, 24)
+
+    def settings(debug):
+        return GaussianRasterizationSettings(image_height=24, image_width=32, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                                             bg=torch.zeros(3), scale_modifier=1.0, viewmatrix=torch.tensor(cam.viewmatrix).reshape(1, 4, 4),
+                                             projmatrix=torch.tensor(cam.projmatrix).reshape(1, 4, 4), sh_degree=0,
+                                             campos=torch.tensor(cam.campos), prefiltered=False, debug=debug)
+    z = torch.rand(5, 3)
+    kw = dict(means3D=z, means2D=torch.zeros(5, 3), opacities=torch.ones(5, 1), colors_precomp=z, scales=z, rotations=torch.rand(5, 4))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        GaussianRasterizer(raster_settings=settings(False))(**kw)
+    assert not os.path.exists("snapshot_fw.dump")
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        GaussianRasterizer(raster_settings=settings(True))(**kw)
+    snap = torch.load("snapshot_fw.dump")
+    assert torch.equal(snap["means3D"], z) and snap["image_height"] == 24 and snap["sh"] is None

@@ -87,6 +87,17 @@ def _check_pending():
                                "that step (or use TOPO4D_B200_SYNC=1)." % (s.num_instances, s.cap_instances))
 
 
+def _dump_snapshot(path, args, what):
+    """``debug=True`` (helpers.py:86 passes False; upstream's wrapper saves `snapshot_fw.dump` / `snapshot_bw.dump` when the
+    native call throws): write the call's inputs, as CPU copies, next to the process and say so.  Never raises itself."""
+    try:
+        cpu = {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in args.items()}
+        torch.save(cpu, path)
+        print(f"\nAn error occured in {what}. Please forward {path} for debugging.")
+    except Exception:  # noqa: BLE001  (a broken CUDA context cannot be copied from; the original error matters more)
+        pass
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     """V-view op.  Outputs carry the leading V dimension; the single-view wrapper strips it."""
 
@@ -97,11 +108,21 @@ class _RasterizeGaussians(torch.autograd.Function):
         sync = _sync_mode() and not capturing
         if not sync and not capturing:
             _check_pending()
-        color, radii, depth, alpha, state = engine.forward(
-            means3D, opacities, cameras, image_height, image_width, shs=sh, colors_precomp=colors_precomp,
-            scales=scales, rotations=rotations, cov3D_precomp=cov3Ds_precomp, sh_degree=sh_degree,
-            scale_modifier=scale_modifier, debug=debug and not capturing,
-            check="sync" if sync else ("none" if capturing else "deferred"))
+        try:
+            color, radii, depth, alpha, state = engine.forward(
+                means3D, opacities, cameras, image_height, image_width, shs=sh, colors_precomp=colors_precomp,
+                scales=scales, rotations=rotations, cov3D_precomp=cov3Ds_precomp, sh_degree=sh_degree,
+                scale_modifier=scale_modifier, debug=debug and not capturing,
+                check="sync" if sync else ("none" if capturing else "deferred"))
+        except Exception:
+            if debug:
+                # upstream's debug contract: on a failing forward, leave the inputs behind for a post-mortem
+                _dump_snapshot("snapshot_fw.dump", dict(means3D=means3D, sh=sh, colors_precomp=colors_precomp, opacities=opacities,
+                                                        scales=scales, rotations=rotations, cov3Ds_precomp=cov3Ds_precomp,
+                                                        cameras=cameras, image_height=image_height, image_width=image_width,
+                                                        sh_degree=sh_degree, scale_modifier=scale_modifier), "forward")
+            raise
+        ctx.debug = bool(debug)
         if capturing:
             _CAPTURE_LOG.append(state)
         elif not sync:
@@ -115,7 +136,15 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
         state = ctx.state
-        g = engine.backward(state, grad_color, grad_depth, grad_alpha)
+        try:
+            g = engine.backward(state, grad_color, grad_depth, grad_alpha)
+        except Exception:
+            if ctx.debug:
+                _dump_snapshot("snapshot_bw.dump", dict(zip(("means3D", "opacities", "sh", "colors_precomp", "scales", "rotations",
+                                                             "cov3Ds_precomp", "cameras"), state.keep),
+                                                        grad_color=grad_color, grad_depth=grad_depth, grad_alpha=grad_alpha,
+                                                        radii=state.radii), "backward")
+            raise
         s = ctx.shapes
         rs = lambda t, shp: None if (t is None or shp is None) else t.reshape(shp)
         return (rs(g.means3D, s[0]), rs(g.means2D, s[1]), rs(g.shs, s[2]), rs(g.colors_precomp, s[3]),
