@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--blend-px", type=int, default=0, help="force the blend kernels' pixels per thread (0 = auto)")
+    ap.add_argument("--verify", action="store_true", help="also at N = 1: compare the step's gradient buffer with an independent "
+                    "single-launch pass over all views (always done when N > 1)")
     return ap.parse_args()
 
 
@@ -305,6 +307,39 @@ def run_ours(a):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
     clocks = sampler.stop() if sampler else None
 
+    # ---- on-hardware check of the multi-GPU result: the all-reduced flat buffer of the view-parallel step must equal the
+    # gradient of ONE process rendering all the views (per segment, |d| / (|ref| + 1e-3 max|ref|), max over ranks) ----
+    verify = None
+    if world > 1 or a.verify:
+        got = step(t).clone()
+        cam_full = cam_all.contiguous()
+        color, radii, depth, alpha, st = engine.forward(t["means3D"], t["opacities"], cam_full, H, W, shs=t.get("shs"),
+                                                        colors_precomp=t.get("colors_precomp"), scales=t["scales"],
+                                                        rotations=t["rotations"], sh_degree=a.sh_degree if use_sh else 0)
+        # the same dL/dpixel images the owning ranks used: regenerate every rank's targets from its seed
+        gC = torch.empty_like(color)
+        for r in range(world):
+            gen_r = torch.Generator(device=dev).manual_seed(1234 + r)
+            views_r = parallel.shard_views(a.views, r, world)
+            grp = [views_r[i:i + vpl] for i in range(0, len(views_r), vpl)]
+            for gv in grp:
+                target = torch.rand((len(gv), 3, H, W), device=dev, generator=gen_r)
+                gC[gv] = torch.sign(color[gv] - target) / (3 * H * W)
+        ref = engine.backward(st, gC, torch.full_like(depth, 0.1 / (H * W)), torch.full_like(alpha, 0.1 / (H * W))).flat
+        M = int(t["shs"].shape[1]) if use_sh else 0
+        va, vb = engine.flat_views(got, a.gaussians, M, use_sh, False), engine.flat_views(ref, a.gaussians, M, use_sh, False)
+        errs = {}
+        for k in va:
+            scale = float(vb[k].abs().max())
+            errs[k] = float(((va[k] - vb[k]).abs() / (vb[k].abs() + 1e-3 * scale + 1e-30)).max())
+        worst = torch.tensor([max(errs.values())], device=dev)
+        if world > 1:
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        verify = {"grad_relerr_vs_single_gpu": float(worst.item()), "per_tensor_rank0": errs, "tolerance": 1e-4,
+                  "what": f"flat gradient buffer after the {world}-rank all-reduce vs one process rendering all {a.views} views "
+                          "(fp32 sums in a different order)"}
+        del color, depth, alpha, st, gC, ref, got
+
     # overflow check after the timed region (capacity was fixed; the flag is sticky per workspace)
     *_, st = fwd(0, t)
     assert not st.status().overflow, "instance capacity overflow during the benchmark"
@@ -359,6 +394,8 @@ def run_ours(a):
                                           "mean_n_contrib_covered_pixels": (stats["n_contrib_sum"] / stats["covered_pixels"])
                                           if stats["covered_pixels"] else None}),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof}
+        if verify is not None:
+            line["verify"] = verify
         if world == 1 and not a.no_cpu_baseline:
             nv = max(1, min(a.cpu_sample_views, a.views))
             from oracle import gs_oracle

@@ -60,14 +60,14 @@ def run_oracle(scene, cams, H, W, sh_degree, bg, g_color=None, g_depth=None, g_a
     return outs, (None if g_color is None else oracle_backward(outs, g_color, g_depth, g_alpha))
 
 
-def cuda_forward(scene, cams, H, W, sh_degree, bg, scale_modifier=1.0, device="cuda:0"):
+def cuda_forward(scene, cams, H, W, sh_degree, bg, scale_modifier=1.0, device="cuda:0", blend_px=None):
     dev = torch.device(device)
     t = {k: torch.tensor(v, device=dev) for k, v in scene.items()}
     cam_t = torch.tensor(engine.pack_cameras_numpy(cams, bg), device=dev)
     color, radii, depth, alpha, st = engine.forward(
         t["means3D"], t["opacities"], cam_t, H, W, shs=t.get("shs"), colors_precomp=t.get("colors_precomp"),
         scales=t.get("scales"), rotations=t.get("rotations"), cov3D_precomp=t.get("cov3D_precomp"),
-        sh_degree=sh_degree, scale_modifier=scale_modifier)
+        sh_degree=sh_degree, scale_modifier=scale_modifier, blend_px=blend_px)
     return dict(color=color, radii=radii, depth=depth, alpha=alpha, state=st)
 
 
@@ -86,8 +86,13 @@ def run_cuda(scene, cams, H, W, sh_degree, bg, g_color=None, g_depth=None, g_alp
     return out, (None if g_color is None else cuda_backward(out, g_color, g_depth, g_alpha))
 
 
+# Oracle results of the large cases, keyed by the caller's `cache_key`: the full-size config-2 tests run the CUDA path
+# several times (blend_px = 1 / 2 / 4) against ONE oracle pass (the oracle is the slow side: seconds per 1080p view).
+_ORACLE_CACHE: dict = {}
+
+
 def compare(scene, cams, H, W, sh_degree=0, bg=(0.0, 0.0, 0.0), seed=1, with_backward=True, scale_modifier=1.0,
-            device="cuda:0", noise_floor=False) -> dict:
+            device="cuda:0", noise_floor=False, blend_px=None, cache_key=None) -> dict:
     """Returns a flat dict of metrics (see keys below); asserts nothing.
 
     Pixels whose discrete threshold decisions (alpha < 1/255, T(1-alpha) < 1e-4) flipped between the two
@@ -95,8 +100,13 @@ def compare(scene, cams, H, W, sh_degree=0, bg=(0.0, 0.0, 0.0), seed=1, with_bac
     comparisons: their loss gradients are zeroed for both sides before the backward passes."""
     V = len(cams)
     rng = np.random.default_rng(seed)
-    ref = oracle_forward(scene, cams, H, W, sh_degree, bg, scale_modifier)
-    out = cuda_forward(scene, cams, H, W, sh_degree, bg, scale_modifier, device)
+    if cache_key is not None and ("fwd", cache_key) in _ORACLE_CACHE:
+        ref = _ORACLE_CACHE[("fwd", cache_key)]
+    else:
+        ref = oracle_forward(scene, cams, H, W, sh_degree, bg, scale_modifier)
+        if cache_key is not None:
+            _ORACLE_CACHE[("fwd", cache_key)] = ref
+    out = cuda_forward(scene, cams, H, W, sh_degree, bg, scale_modifier, device, blend_px)
     m = {}
     view = out["state"].view()
     m["num_rendered_ref"] = int(sum(r["state"].num_rendered for r in ref))
@@ -147,9 +157,15 @@ def compare(scene, cams, H, W, sh_degree=0, bg=(0.0, 0.0, 0.0), seed=1, with_bac
         gC = rng.normal(size=(V, 3, H, W)).astype(np.float32) * keep
         gD = rng.normal(size=(V, 1, H, W)).astype(np.float32) * keep
         gA = rng.normal(size=(V, 1, H, W)).astype(np.float32) * keep
-        ref_g = oracle_backward(ref, gC, gD, gA)
+        bkey = ("bwd", cache_key, seed, bool(noise_floor), hash(flips.tobytes())) if cache_key is not None else None
+        if bkey is not None and bkey in _ORACLE_CACHE:
+            ref_g, ref_f32 = _ORACLE_CACHE[bkey]
+        else:
+            ref_g = oracle_backward(ref, gC, gD, gA)
+            ref_f32 = oracle_backward(ref, gC, gD, gA, f32_replay=True) if noise_floor else None
+            if bkey is not None:
+                _ORACLE_CACHE[bkey] = (ref_g, ref_f32)
         g = cuda_backward(out, gC, gD, gA)
-        ref_f32 = oracle_backward(ref, gC, gD, gA, f32_replay=True) if noise_floor else None
         for k, a in ref_g.items():
             if k == "acc2d":
                 continue

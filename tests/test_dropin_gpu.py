@@ -107,3 +107,20 @@ def test_async_mode_defers_the_overflow_check(monkeypatch):
     ref_s, _ = parity.run_oracle(dict(sc, scales=sc["scales"] * 0.2), [cam], 80, 112, 0, (0, 0, 0))
     assert np.abs(small.cpu().numpy() - ref_s[0]["color"]).max() <= parity.ABS_TOL
     rasterizer._PENDING.clear()
+
+
+def test_inplace_edit_between_forward_and_backward_raises():
+    """The kernels re-read the inputs in backward (nothing but pointers is stored), so an in-place edit of an input
+    between forward and backward must raise autograd's version-counter error -- as it does with upstream's wrapper,
+    which saves its inputs with save_for_backward -- instead of silently producing gradients of the modified values."""
+    from diff_gaussian_rasterization import GaussianRasterizer as Renderer
+    sc = synth.random_scene(500, seed=4)
+    cam = synth.front_camera(64, 48)
+    p = {k: torch.tensor(v, device="cuda", requires_grad=True) for k, v in sc.items()}
+    scales = p["scales"] * 1.0                       # non-leaf, so an in-place edit is legal for autograd itself
+    im, *_ = Renderer(raster_settings=_settings(cam, (0.0, 0.0, 0.0)))(
+        means3D=p["means3D"], means2D=torch.zeros_like(p["means3D"]), colors_precomp=p["colors_precomp"],
+        rotations=p["rotations"], opacities=p["opacities"], scales=scales)
+    scales.mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        im.sum().backward()

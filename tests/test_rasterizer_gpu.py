@@ -207,3 +207,38 @@ def test_repeated_backward_and_staged_forward_reuse_the_work_queues():
     tol = 1e-5 * float(g1.abs().max())
     assert float(g1.abs().max()) > 0
     assert torch.allclose(g1, g2, rtol=1e-4, atol=tol) and torch.allclose(g1, g3, rtol=1e-4, atol=tol)
+
+
+# ---- BASELINE config 2 at FULL size: the workload bench.py times (60 k mesh-bound Gaussians, SH degree 3, 1920x1080) ----
+_CFG2_VIEWS = (0, 7, 13, 20)          # both camera rings, four azimuths
+# Flip budget at this size, stated: at most 1 pixel per 100 000 may differ in a discrete threshold decision
+# (alpha < 1/255, T(1-alpha) < 1e-4 -- a 1-ulp exp() event); flipped pixels are counted, excluded from the value
+# comparison and their loss gradients zeroed on both sides (tests/parity.py).  4 views x 2 073 600 px -> <= 82.
+_CFG2_FLIPS = len(_CFG2_VIEWS) * 1920 * 1080 // 100000
+
+
+def _cfg2(opacity):
+    scene = synth.head_scene(60000, seed=0, sh_degree=3, opacity=opacity)
+    cams = [synth.ring_cameras(24)[i] for i in _CFG2_VIEWS]
+    return scene, cams
+
+
+@pytest.mark.parametrize("opacity", ["topo4d", "generic"])
+@pytest.mark.parametrize("px", [2, 4, 1])
+def test_config2_full_size_parity(opacity, px):
+    """SURVEY 8(d) configs 2-3, both opacity regimes ("topo4d" = 1.0, "generic" = U(0.3, 1)), with the blend kernels'
+    pixels-per-thread variant forced to each of 1 / 2 / 4 (bench.py's 24-view launch runs PX = 2).  Tolerances: RGB /
+    depth / alpha <= 1e-4 abs, gradients <= 1e-3 rel (or the all-fp32 algorithm's own noise floor where the 0.99 cap makes
+    that larger), radii / tile ranges / sorted lists bit-exact, flips <= _CFG2_FLIPS."""
+    scene, cams = _cfg2(opacity)
+    m = parity.compare(scene, cams, 1080, 1920, 3, (0.0, 0.0, 0.0), noise_floor=True, blend_px=px, cache_key="cfg2-" + opacity)
+    assert m["num_rendered"] > 400000
+    parity.assert_parity(m, allow_flips=_CFG2_FLIPS)
+
+
+def test_config2_full_size_background_and_auto_px():
+    """Same scene, non-zero background, blend_px chosen by the engine's heuristic (second call of the shape)."""
+    scene, cams = _cfg2("generic")
+    for _ in range(2):
+        m = parity.compare(scene, cams[:2], 1080, 1920, 3, (0.2, 0.5, 0.8), cache_key="cfg2-generic-bg")
+        parity.assert_parity(m, allow_flips=_CFG2_FLIPS)

@@ -95,12 +95,20 @@ def lib_path() -> str:
 
 
 def lib():
-    """Load (building in-tree if stale/missing) the CUDA library.  Raises if that is impossible."""
+    """Load the CUDA library, (re)building it in-tree when it is missing or does not match its sources' content hash.
+    Raises if that is impossible."""
     global _LIB
     if _LIB is None:
         path = os.environ.get("TOPO4D_B200_LIB") or _build.LIB_PATH      # override: experiment variants (build.py --tag)
-        if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("TOPO4D_B200_REBUILD") == "1"):
-            path = _build.build_library()
+        if path == _build.LIB_PATH:
+            # build_library() returns at once when the library matches the content hash of its sources; a stale binary
+            # (edited .cu / header, ctypes structs out of step) is rebuilt -- by one process only under torchrun
+            if int(os.environ.get("LOCAL_RANK", "0")) == 0 or not os.path.exists(path):
+                path = _build.build_library(force=os.environ.get("TOPO4D_B200_REBUILD") == "1")
+            elif _build._stale(path):
+                import warnings
+                warnings.warn("topo4d_b200: libtopo4d_b200.so is older than its sources and this is not local rank 0; "
+                              "loading it as is (run `python -m topo4d_b200.build`)")
         handle = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)        # AttributeError if the symbol is missing

@@ -43,18 +43,34 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def _stale(lib_path: str) -> bool:
+def _source_hash(defines: list[str] | None = None) -> str:
+    """Content hash of everything the library is built from (sources, header, this recipe, extra defines).  A content
+    hash rather than mtimes: the tree travels to the GPU box as a snapshot whose file times mean nothing."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(_HERE, "..", "include", "topo4d_b200.h"),
+                                                                      os.path.abspath(__file__)]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(defines or []).encode())
+    return h.hexdigest()
+
+
+def _stale(lib_path: str, defines: list[str] | None = None) -> bool:
     if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(lib_path)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "topo4d_b200.h"),
-                                                                os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(lib_path + ".srchash") as f:
+            return f.read().strip() != _source_hash(defines)
+    except OSError:
+        return True
 
 
 def build_library(force: bool = False, verbose: bool = False, tag: str = "", defines: list[str] | None = None) -> str:
     lib_path = LIB_PATH if not tag else os.path.join(OUT_DIR, f"libtopo4d_b200_{tag}.so")
-    if not force and not _stale(lib_path):
+    if not force and not _stale(lib_path, defines):
         return lib_path
     obj_dir = OUT_DIR if not tag else os.path.join(OUT_DIR, tag)
     os.makedirs(obj_dir, exist_ok=True)
@@ -75,10 +91,14 @@ def build_library(force: bool = False, verbose: bool = False, tag: str = "", def
             print(out, file=sys.stderr)
         if pr.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    link = [nvcc, *ARCH, "-shared", "-o", lib_path, *objs]
+    tmp = lib_path + f".tmp{os.getpid()}"
+    link = [nvcc, *ARCH, "-shared", "-o", tmp, *objs]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")
+    os.replace(tmp, lib_path)                 # atomic: a concurrent loader sees the old or the new library, never half of one
+    with open(lib_path + ".srchash", "w") as f:
+        f.write(_source_hash(defines))
     return lib_path
 
 

@@ -12,10 +12,6 @@
 // gradient where clamped, depth = view-space z, mean2D gradient reported x(0.5W, 0.5H).
 #include "gs_common.cuh"
 
-// Build-time experiment, off by default (see gs_preprocess.cu); the default build's SASS is unchanged by its presence.
-#ifndef GS_PBWD_QUAD_STORES
-#define GS_PBWD_QUAD_STORES 0
-#endif
 
 namespace {
 
@@ -241,34 +237,15 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
             for (int k = 0; k < KK * 3; k++) gsh[k] += __shfl_xor_sync(0xffffffffu, gsh[k], o);
         }
     }
-#if GS_PBWD_QUAD_STORES
-    // EXPERIMENT (default off, unmeasured): after the butterfly all four lanes of a quad hold the full SH sums, so each
-    // lane writes a quarter of the 48 floats as 16-byte stores (instead of 48 strided 4-byte stores by lane 0 alone).
-    if constexpr (K == 16) {
-        if (act && p.M == 16) {
-            float4* __restrict__ o4 = reinterpret_cast<float4*>(io.dL_dshs + (size_t)i * 48);
-            #pragma unroll
-            for (int q4 = 0; q4 < 4; q4++) {
-                if (vq == q4) {
-                    #pragma unroll
-                    for (int j = 0; j < 3; j++)
-                        o4[3 * q4 + j] = make_float4(gsh[12 * q4 + 4 * j], gsh[12 * q4 + 4 * j + 1], gsh[12 * q4 + 4 * j + 2], gsh[12 * q4 + 4 * j + 3]);
-                }
-            }
-        }
-    }
-#endif
     if (!act || vq != 0) return;
     io.dL_dmeans3D[3 * i] = gm[0]; io.dL_dmeans3D[3 * i + 1] = gm[1]; io.dL_dmeans3D[3 * i + 2] = gm[2];
     io.dL_dmeans2D[3 * i] = gm2[0]; io.dL_dmeans2D[3 * i + 1] = gm2[1]; io.dL_dmeans2D[3 * i + 2] = 0.f;
     io.dL_dopacities[i] = gop;
     if constexpr (K > 0) {
         float* __restrict__ o = io.dL_dshs + (size_t)i * p.M * 3;
-        if (!(GS_PBWD_QUAD_STORES && K == 16 && p.M == 16)) {
-            #pragma unroll
-            for (int k = 0; k < KK * 3; k++) o[k] = gsh[k];
-            for (int k = KK * 3; k < p.M * 3; k++) o[k] = 0.f;
-        }
+        #pragma unroll
+        for (int k = 0; k < KK * 3; k++) o[k] = gsh[k];
+        for (int k = KK * 3; k < p.M * 3; k++) o[k] = 0.f;
     } else {
         io.dL_dcolors[3 * i] = gcol[0]; io.dL_dcolors[3 * i + 1] = gcol[1]; io.dL_dcolors[3 * i + 2] = gcol[2];
     }

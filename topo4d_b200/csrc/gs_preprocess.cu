@@ -14,12 +14,6 @@
 //     stable (tile|depth) radix sort produces -- so no host sync is needed to size buffers.
 #include "gs_common.cuh"
 
-// Build-time experiments (python -m topo4d_b200.build --tag NAME -DGS_...=1, compared with tools/variants.py); all off by
-// default, and the default build's SASS is unchanged by their presence.
-#ifndef GS_SCATTER_BATCH
-#define GS_SCATTER_BATCH 0
-#endif
-
 namespace {
 
 __device__ __constant__ float kC0 = 0.28209479177387814f;
@@ -212,33 +206,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(const GsParams p, const in
     const Rect rc = tile_rect(g0.x, g0.y, (float)rad, p.tiles_x, p.tiles_y);
     const unsigned long long pair = ((unsigned long long)__float_as_uint(g1.z) << 32) | (unsigned)i;
     const size_t tbase = (size_t)v * p.tiles;
-#if GS_SCATTER_BATCH
-    // EXPERIMENT (default off, unmeasured): the cursor atomics of up to four tiles are issued back to back before the
-    // first position is needed, instead of one exposed L2 round trip per tile (most splats cover 1-4 tiles).
-    const int w = rc.maxx - rc.minx, ntile = w * (rc.maxy - rc.miny);
-    for (int b = 0; b < ntile; b += 4) {
-        unsigned long long pos[4];
-        #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int e = b + k;
-            pos[k] = ~0ull;
-            if (e < ntile) {
-                const size_t t = tbase + (size_t)(rc.miny + e / w) * p.tiles_x + (rc.minx + e % w);
-                pos[k] = (unsigned long long)p.tile_start[t] + atomicAdd(p.tile_fill + t, 1u);
-            }
-        }
-        #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (pos[k] < (unsigned long long)p.cap) p.pairs[pos[k]] = pair;
-    }
-#else
     for (int y = rc.miny; y < rc.maxy; y++)
         for (int x = rc.minx; x < rc.maxx; x++) {
             const size_t t = tbase + y * p.tiles_x + x;
             const unsigned long long pos = (unsigned long long)p.tile_start[t] + atomicAdd(p.tile_fill + t, 1u);
             if (pos < (unsigned long long)p.cap) p.pairs[pos] = pair;
         }
-#endif
 }
 
 __global__ void mark_visible_kernel(int N, const float* __restrict__ means3D, const float* __restrict__ cam,

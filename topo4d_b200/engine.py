@@ -275,6 +275,32 @@ def _al4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+def flat_layout(N: int, M: int, use_sh: bool, use_cov: bool):
+    """Segment offsets (in floats, each 16-byte aligned) of the flat gradient buffer: means3D | means2D | colour or SH |
+    opacities | scales or cov3D | rotations.  Returns ({name: (offset, size)}, total)."""
+    ncol = N * M * 3 if use_sh else N * 3
+    sizes = [("means3D", N * 3), ("means2D", N * 3), ("color", ncol), ("opacities", N),
+             ("a", N * 6 if use_cov else N * 3), ("b", 0 if use_cov else N * 4)]
+    offs, o = {}, 0
+    for name, n in sizes:
+        offs[name] = (o, n)
+        o += _al4(n)
+    return offs, max(o, 4)
+
+
+def flat_views(flat: torch.Tensor, N: int, M: int, use_sh: bool, use_cov: bool) -> dict:
+    """Named views of a flat gradient buffer laid out by :func:`flat_layout` (keys as the op's keyword arguments)."""
+    offs, _ = flat_layout(N, M, use_sh, use_cov)
+    seg = {k: flat[s:s + n] for k, (s, n) in offs.items()}
+    out = {"means3D": seg["means3D"].view(N, 3), "means2D": seg["means2D"].view(N, 3), "opacities": seg["opacities"].view(N, 1)}
+    out["shs" if use_sh else "colors_precomp"] = seg["color"].view(N, M, 3) if use_sh else seg["color"].view(N, 3)
+    if use_cov:
+        out["cov3D_precomp"] = seg["a"].view(N, 6)
+    else:
+        out["scales"], out["rotations"] = seg["a"].view(N, 3), seg["b"].view(N, 4)
+    return out
+
+
 def backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None, flat: torch.Tensor | None = None,
              stage_events=None) -> GradBundle:
     """Gradients summed over the V views of `state`.  dL_dcolor [V,3,H,W] (or [3,H,W] when V == 1)."""
@@ -284,14 +310,7 @@ def backward(state: RasterState, dL_dcolor, dL_ddepth=None, dL_dalpha=None, flat
     dL_ddepth = _f32c(dL_ddepth, dev)
     dL_dalpha = _f32c(dL_dalpha, dev)
     assert dL_dcolor.numel() == V * 3 * H * W, "dL_dcolor must be [V,3,H,W]"
-    ncol = N * M * 3 if state.use_sh else N * 3
-    sizes = [("means3D", N * 3), ("means2D", N * 3), ("color", ncol), ("opacities", N),
-             ("a", N * 6 if state.use_cov else N * 3), ("b", 0 if state.use_cov else N * 4)]
-    offs, o = {}, 0
-    for name, n in sizes:
-        offs[name] = (o, n)
-        o += _al4(n)
-    total = max(o, 4)
+    offs, total = flat_layout(N, M, state.use_sh, state.use_cov)
     if flat is None:
         flat = torch.zeros(total, dtype=torch.float32, device=dev) if N == 0 else \
             torch.empty(total, dtype=torch.float32, device=dev)

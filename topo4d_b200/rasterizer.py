@@ -128,6 +128,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         elif not sync:
             _PENDING.append(state)
         ctx.state = state
+        # The kernels re-read the inputs through the raw pointers held in `state` when the backward runs (cov3D, J and T are
+        # recomputed, not stored).  Saving the tensors makes autograd's version counters guard them: an in-place edit
+        # between forward and backward raises the usual "modified by an inplace operation" error, as upstream's wrapper does.
+        ctx.save_for_backward(*[t for t in (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, cameras)
+                                if torch.is_tensor(t)])
         ctx.shapes = tuple(None if t is None else t.shape for t in
                            (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
         ctx.mark_non_differentiable(radii)
@@ -136,6 +141,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
         state = ctx.state
+        ctx.saved_tensors                      # version-counter check of every input the kernels are about to re-read
         try:
             g = engine.backward(state, grad_color, grad_depth, grad_alpha)
         except Exception:
