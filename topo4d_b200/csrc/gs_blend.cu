@@ -63,6 +63,10 @@ constexpr int WPC = GS_WPC;
 #ifndef GS_FWD_MINB
 #define GS_FWD_MINB (28 / GS_WPC)
 #endif
+// PX = 2 backward: 1 = warp reduction on the tensor pipe (blend_bwd_mma_kernel), 0 = shared-memory transpose (blend_bwd_kernel<2>)
+#ifndef GS_BWD_MMA
+#define GS_BWD_MMA 1
+#endif
 constexpr uint32_t REC_BYTES = 48;
 [[maybe_unused]] constexpr float LOG2E = 1.4426950408889634f;
 
@@ -138,12 +142,35 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float x)
 {
     asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(x) : "memory");
 }
+// two fp32 lanes in one 64-bit register: shared-memory load / store and the packed add (SASS FADD2, sm_100)
 template <int OFF>
-__device__ __forceinline__ float lds_f32(uint32_t addr)
+__device__ __forceinline__ unsigned long long lds_b64(uint32_t addr)
 {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF) : "memory");
+    unsigned long long v;
+    asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(v) : "r"(addr), "n"(OFF) : "memory");
     return v;
+}
+__device__ __forceinline__ void sts_b64(uint32_t addr, unsigned long long v)
+{
+    asm volatile("st.shared.b64 [%0], %1;" :: "r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long shfl_xor_b64(unsigned long long v, int m)
+{
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+// index of the most significant set bit (x != 0): one FLO instead of the clz / 31-x pair __clz compiles to
+__device__ __forceinline__ int msb_index(unsigned x)
+{
+    int j;
+    asm("bfind.u32 %0, %1;" : "=r"(j) : "r"(x));
+    return j;
 }
 
 // ---- work queues ----
@@ -377,12 +404,13 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
     __syncwarp();
     uint32_t phases = 0u;
     const size_t HW = (size_t)p.H * p.W;
-    // reduction addresses (see below): where this lane parks its partial record, the column it sums, its result slot
-    const int red_c = lane & 15, red_h = lane >> 4;
-    const bool red_on = red_c < GS_REC_FLOATS;
+    // reduction addresses (see below): where this lane parks its partial record, the column PAIR it sums over the rows
+    // q, q + 4, ..., its result slot
+    const int red_cp = lane & 7, red_q = lane >> 3;           // (conflict-free for 8-byte loads: each half-warp reads 24 consecutive words)
+    const bool red_on = red_cp < GS_REC_FLOATS / 2;
     const uint32_t a_park = pinned_smem_addr(&s_tr[warp][lane * GS_REC_FLOATS]);
-    const uint32_t a_col = pinned_smem_addr(&s_tr[warp][red_h * GS_REC_FLOATS + (red_on ? red_c : 0)]);
-    const uint32_t a_out = pinned_smem_addr(&s_acc[warp][red_on ? red_c : 0]);
+    const uint32_t a_col = pinned_smem_addr(&s_tr[warp][red_q * GS_REC_FLOATS + (red_on ? 2 * red_cp : 0)]);
+    const uint32_t a_out = pinned_smem_addr(&s_acc[warp][red_on ? 2 * red_cp : 0]);
     const float4* __restrict__ my_acc = reinterpret_cast<const float4*>(s_acc[warp]);
 
     for (;;) {
@@ -453,11 +481,14 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
             // warp-level compaction (see the forward): only records whose reach mask meets this warp's 8x4 blocks are
             // walked, back to front
             unsigned live = __ballot_sync(0xffffffffu, lane < cnt && ((recw[lane * 12 + 11] >> 24) & my_blocks) != 0u);
-            unsigned touched = 0u;                              // warp-uniform: records whose moments sit in s_acc
+            unsigned touched = live;                            // warp-uniform: records whose moments will sit in s_acc
+            int lastc[PX];                                      // pixel k contributes to records j < lastc[k] of this chunk
+            #pragma unroll
+            for (int k = 0; k < PX; k++) lastc[k] = (int)last[k] - c * CHUNK;
             while (live) {                                      // warp-uniform
-                const int j = 31 - __clz(live);
-                live ^= 1u << j;
-                const uint32_t idx = (uint32_t)(c * CHUNK + j);
+                const int j = msb_index(live);
+                const unsigned jbit = 1u << j;
+                live ^= jbit;
                 const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
                 const float dx = __fsub_rn(r0.x, pxf);
                 const ColTerms ct = col_terms(r0.z, r0.w, r1.x, dx);
@@ -467,74 +498,69 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                 for (int k = 0; k < PX; k++) {
                     dyr[k] = __fsub_rn(r0.y, pyf[k]);
                     pw[k] = splat_power(ct, dyr[k]);
-                    hit[k] = pw[k] >= r1.w && idx < last[k];           // the (rare) power > 0 skip is tested on the blend path
+                    hit[k] = pw[k] >= r1.w && j < lastc[k];            // the (rare) power > 0 skip is tested on the blend path
                     any = any || hit[k];
                 }
-                if (!__any_sync(0xffffffffu, any)) continue;
+                if (!__any_sync(0xffffffffu, any)) { touched ^= jbit; continue; }
                 // moments of t = G dL/dalpha over this thread's pixels: {t dx, t dy, t dx^2, t dx dy | t dy^2, t, w g_d, - | w g_rgb}
                 float r[10];
                 #pragma unroll
                 for (int s = 0; s < 10; s++) r[s] = 0.f;
-                if (any) {
-                    const float4 r2 = rec[j * 3 + 2];
-                    #pragma unroll
-                    for (int k = 0; k < PX; k++) {
-                        if (hit[k]) {
-                            const float G = splat_exp(pw[k]);
-                            const float alpha = splat_alpha(r1.y, G);
-                            if (alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f) {
-                                // the recovery T_i = T_{i+1} * (1/(1-alpha)) is replayed once per contributing layer (thousands
-                                // for very deep lists): a bare approximate reciprocal is biased and drifts past 1e-3, a
-                                // Newton-refined one does not (and __frcp_rn costs 15 % of the kernel)
-                                const float om = __fsub_rn(1.0f, alpha);             // in [0.01, 1]
-                                float ra;
-                                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(om));
-                                ra = __fmaf_rn(__fmaf_rn(-om, ra, 1.0f), ra, ra);    // one Newton step: <= 1 ulp, unbiased
-                                const float Tk = __fmul_rn(T[k], ra);            // undoes the forward's T*(1-alpha)
-                                const float w = __fmul_rn(alpha, Tk);
-                                // dL/dalpha_i = T_i (g . x_i) - (g . suffix_i + T_final bg.g) / (1 - alpha_i),  x_i = (rgb, depth, 1)
-                                const float Pk = __fmaf_rn(g0[k], r2.x, __fmaf_rn(g1[k], r2.y, __fmaf_rn(g2[k], r2.z, __fmaf_rn(gd[k], r1.z, ga[k]))));
-                                const float dLda = Tk * Pk - ra * Q[k];
-                                Q[k] = __fmaf_rn(w, Pk, Q[k]);
-                                // dL/dG * G = opacity * t (straight-through the 0.99 cap); the opacity, the conic entries and
-                                // the -1/2 factors are constants of the record and are applied once, after the reduction
-                                const float t = G * dLda;
-                                const float tx = t * dx, ty = t * dyr[k];
-                                r[0] += tx;
-                                r[1] += ty;
-                                r[2] = __fmaf_rn(tx, dx, r[2]);
-                                r[3] = __fmaf_rn(tx, dyr[k], r[3]);
-                                r[4] = __fmaf_rn(ty, dyr[k], r[4]);
-                                r[5] += t;
-                                r[6] = __fmaf_rn(w, gd[k], r[6]);
-                                r[7] = __fmaf_rn(w, g0[k], r[7]); r[8] = __fmaf_rn(w, g1[k], r[8]); r[9] = __fmaf_rn(w, g2[k], r[9]);
-                                T[k] = Tk;
-                            }
+                const float4 r2 = rec[j * 3 + 2];
+                #pragma unroll
+                for (int k = 0; k < PX; k++) {
+                    if (hit[k]) {
+                        const float G = splat_exp(pw[k]);
+                        const float alpha = splat_alpha(r1.y, G);
+                        if (alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f) {
+                            // the recovery T_i = T_{i+1} * (1/(1-alpha)) is replayed once per contributing layer (thousands
+                            // for very deep lists): a bare approximate reciprocal is biased and drifts past 1e-3, a
+                            // Newton-refined one does not (and __frcp_rn costs 15 % of the kernel)
+                            const float om = __fsub_rn(1.0f, alpha);             // in [0.01, 1]
+                            float ra;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(om));
+                            ra = __fmaf_rn(__fmaf_rn(-om, ra, 1.0f), ra, ra);    // one Newton step: <= 1 ulp, unbiased
+                            const float Tk = __fmul_rn(T[k], ra);            // undoes the forward's T*(1-alpha)
+                            const float w = __fmul_rn(alpha, Tk);
+                            // dL/dalpha_i = T_i (g . x_i) - (g . suffix_i + T_final bg.g) / (1 - alpha_i),  x_i = (rgb, depth, 1)
+                            const float Pk = __fmaf_rn(g0[k], r2.x, __fmaf_rn(g1[k], r2.y, __fmaf_rn(g2[k], r2.z, __fmaf_rn(gd[k], r1.z, ga[k]))));
+                            const float dLda = Tk * Pk - ra * Q[k];
+                            Q[k] = __fmaf_rn(w, Pk, Q[k]);
+                            // dL/dG * G = opacity * t (straight-through the 0.99 cap); the opacity, the conic entries and
+                            // the -1/2 factors are constants of the record and are applied once, after the reduction
+                            const float t = G * dLda;
+                            const float tx = t * dx, ty = t * dyr[k];
+                            r[0] += tx;
+                            r[1] += ty;
+                            r[2] = __fmaf_rn(tx, dx, r[2]);
+                            r[3] = __fmaf_rn(tx, dyr[k], r[3]);
+                            r[4] = __fmaf_rn(ty, dyr[k], r[4]);
+                            r[5] += t;
+                            r[6] = __fmaf_rn(w, gd[k], r[6]);
+                            r[7] = __fmaf_rn(w, g0[k], r[7]); r[8] = __fmaf_rn(w, g1[k], r[8]); r[9] = __fmaf_rn(w, g2[k], r[9]);
+                            T[k] = Tk;
                         }
                     }
                 }
                 // warp reduction through shared memory: every lane parks its 12-float partial record (three 16-byte
-                // stores, conflict-free), then lane (c, h) = (lane & 15, lane >> 4) sums column c over rows 2i+h
-                // (16 conflict-free loads) and one shuffle joins the halves: ~40 instructions instead of a 16-shuffle /
-                // 32-select butterfly (~70).
+                // stores, conflict-free), then lane (cp, q) = (lane & 7, lane >> 3) sums the column pair cp over the rows
+                // q + 4i with eight 8-byte loads and packed adds (FADD2), and two packed shuffle steps join the four row
+                // classes: ~26 instructions per record instead of ~41 for scalar column sums (or ~70 for a shuffle
+                // butterfly over ten values).  Lanes with cp > 5 repeat pair 0 and do not store.
                 {
                     sts_v4(a_park, r[0], r[1], r[2], r[3]);
                     sts_v4(a_park + 16, r[4], r[5], r[6], 0.f);
                     sts_v4(a_park + 32, r[7], r[8], r[9], 0.f);
                     __syncwarp();
-                    float acc = 0.f;
-                    if (red_on) {
-                        constexpr int RS = 2 * GS_REC_FLOATS * 4;            // byte stride of two rows
-                        acc = ((lds_f32<0 * RS>(a_col) + lds_f32<1 * RS>(a_col)) + (lds_f32<2 * RS>(a_col) + lds_f32<3 * RS>(a_col))) +
-                              ((lds_f32<4 * RS>(a_col) + lds_f32<5 * RS>(a_col)) + (lds_f32<6 * RS>(a_col) + lds_f32<7 * RS>(a_col)));
-                        acc += ((lds_f32<8 * RS>(a_col) + lds_f32<9 * RS>(a_col)) + (lds_f32<10 * RS>(a_col) + lds_f32<11 * RS>(a_col))) +
-                               ((lds_f32<12 * RS>(a_col) + lds_f32<13 * RS>(a_col)) + (lds_f32<14 * RS>(a_col) + lds_f32<15 * RS>(a_col)));
-                    }
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-                    if (red_h == 0 && red_on) sts_f32(a_out + (uint32_t)j * (GS_REC_FLOATS * 4), acc);
+                    constexpr int RS = 4 * GS_REC_FLOATS * 4;                // byte stride of four rows
+                    unsigned long long acc =
+                        add_f32x2(add_f32x2(add_f32x2(lds_b64<0 * RS>(a_col), lds_b64<1 * RS>(a_col)), add_f32x2(lds_b64<2 * RS>(a_col), lds_b64<3 * RS>(a_col))),
+                                  add_f32x2(add_f32x2(lds_b64<4 * RS>(a_col), lds_b64<5 * RS>(a_col)), add_f32x2(lds_b64<6 * RS>(a_col), lds_b64<7 * RS>(a_col))));
+                    acc = add_f32x2(acc, shfl_xor_b64(acc, 8));
+                    acc = add_f32x2(acc, shfl_xor_b64(acc, 16));
+                    if (red_q == 0 && red_on) sts_b64(a_out + (uint32_t)j * (GS_REC_FLOATS * 4), acc);
                     __syncwarp();
                 }
-                touched |= 1u << j;
             }
             // flush the chunk: moments -> gradients of the 2-D record (pix.x, pix.y, conic A, B, C, opacity, depth, rgb),
             // conic B being the true (not halved) derivative; one 16-byte vector RED per touched (record, part)
@@ -547,6 +573,258 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                 const float o = q1.y;
                 if (part == 0) a = make_float4(-o * (q0.z * a.x + q0.w * a.y), -o * (q1.x * a.y + q0.w * a.x), -0.5f * o * a.z, -o * a.w);
                 else if (part == 1) a.x = -0.5f * o * a.x;
+                const int id = __float_as_int(rec[j * 3 + 2].w) & 0x00ffffff;
+                red_add_v4(gbase + (size_t)id * 3 + part, a);
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) gs_queue_release(&p.status->q_bwd_heavy, &p.status->done_bwd, gridDim.x * WPC);
+}
+
+// ---- PX = 2 backward with the warp reduction on the (otherwise idle) tensor pipe --------------------------------------
+// The shared-memory transpose reduction of blend_bwd_kernel moves 32 lanes x 48 B in and out of shared memory per
+// (record, warp) visit: ncu showed the LSU data pipe at 84 % of its peak (176 M shared-memory wavefronts per 24-view launch),
+// i.e. that kernel is bound by shared-memory bandwidth, not by instruction issue.  Here the lane -> pixel map is
+//     lane = 4 g + t:   pixel 0 = (x, y) = (g, t),  pixel 1 = (g, t + 4)        inside the warp's 8 x 8 pixel block
+// (a vertical comb like blend_bwd_kernel's, so the two pixels still share the column terms of the quadratic form and pixel
+// slot k is still one compact 8 x 4 block), which is exactly the fragment geometry of mma.sync.m16n8k8 (TF32): the four lanes
+// of a quad and the two k-halves are the contraction index (= y, 0..7), g is a free index (= x).  The six geometric moments of
+// a record are polynomial in the pixel coordinates: with tt = G dL/dalpha per pixel and coordinates centred on the block
+// (x', y' = -3.5 .. 3.5, which keeps the later re-centring on the splat well conditioned),
+//     S_n(x) = sum_y tt(x, y) y'^n  (n = 0, 1, 2)     is ONE mma with B[k][.] = (1, k', k'^2),
+// and M1 = sum_x S_0, My = sum_x S_1, Mx = sum_x x' S_0, Mxy = sum_x x' S_1, Myy = sum_x S_2, Mxx = sum_x x'^2 S_0 follow by a per-lane
+// scale (1, x', 1, x'^2 by lane-in-quad; B repeats the S_0 / S_1 columns so every lane receives the pair it scales).  The four
+// colour / depth moments sum_pixels w g_c take two more mma (high and low halves) with a 0/1 selector as B.  TF32 keeps 10
+// mantissa bits, so every fp32 operand is split exactly into hi (upper bits) + lo (remainder): the monomials and selectors are
+// small integers (exact), products are exact, accumulation is fp32 -- measured agreement with an fp32 shuffle reduction: 5e-6
+// worst case, 1e-7 typical (tools/probes/mma_quadsum.cu).  What reaches shared memory is one 12-float row per QUAD (8 rows, 3
+// wavefronts) instead of one per lane (32 rows, 12 wavefronts), and the column sums read 8 rows instead of 32.
+// The moments are taken about the block centre (half-integer coordinates and their squares: exact in TF32); the flush
+// re-centres them on the splat (ex = mean.x - Xc, ey = mean.y - Yc) once per (chunk, record).  About the block CORNER the
+// second moments lost 5x accuracy to cancellation (conic gradients 6.5e-4 instead of 1.3e-4 of the oracle, tools/probe_grad2d.py).
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// exact split of an fp32 into a TF32-representable high part (bit pattern) and the remainder
+__device__ __forceinline__ void split_tf32(float v, unsigned& hi, unsigned& lo)
+{
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(__fsub_rn(v, __uint_as_float(hi)));
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, float x, float y)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(addr), "f"(x), "f"(y) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+
+constexpr int QROW = 8;                       // floats per parked quad row (per part)
+constexpr int QW_OFF = 8 * QROW + 16;         // second part (colour / depth moments) starts 16 banks away from the first
+
+__global__ void __launch_bounds__(WPC * 32, GS_BWD_MINB)
+blend_bwd_mma_kernel(const GsParams p, const GsBackwardIO io)
+{
+    constexpr int PX = 2, NWT = 8 / PX;
+    __shared__ __align__(128) float4 s_rec[WPC][2][CHUNK * 3];
+    __shared__ __align__(16) float s_acc[WPC][CHUNK * GS_REC_FLOATS];   // block-origin moments of the chunk's records
+    __shared__ __align__(16) float s_q[WPC][QW_OFF + 8 * QROW];         // per-quad partial rows of the record being reduced
+    __shared__ __align__(8) uint64_t s_bar[WPC][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 (*const ring)[CHUNK * 3] = s_rec[warp];
+    uint64_t* const bar = s_bar[warp];
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    __syncwarp();
+    uint32_t phases = 0u;
+    const size_t HW = (size_t)p.H * p.W;
+    const int g = lane >> 2, t = lane & 3;                       // mma fragment coordinates = pixel column, pixel row (and + 4)
+    // B operands (TF32 bit patterns of half-integers).  Geometry: columns (S0, S1, S0, S1, S2, 0, S0, 0), lane-in-quad t receives
+    // columns 2t, 2t+1 and scales them by (1, x', 1, x'^2).  Selector: k < 4 -> columns 0 and 4, k >= 4 -> columns 2 and 6.
+    const float ft = (float)t - 3.5f, ft4 = (float)t + 0.5f;
+    const bool c_s0 = g == 0 || g == 2 || g == 6, c_s1 = g == 1 || g == 3, c_s2 = g == 4;
+    unsigned bt0 = __float_as_uint(c_s0 ? 1.f : c_s1 ? ft : c_s2 ? ft * ft : 0.f);
+    unsigned bt1 = __float_as_uint(c_s0 ? 1.f : c_s1 ? ft4 : c_s2 ? ft4 * ft4 : 0.f);
+    unsigned bw0 = __float_as_uint((g == 0 || g == 4) ? 1.f : 0.f), bw1 = __float_as_uint((g == 2 || g == 6) ? 1.f : 0.f);
+    const float fxc = (float)g - 3.5f;
+    float fsel = t == 0 ? 1.f : t == 1 ? fxc : t == 2 ? 1.f : fxc * fxc;
+    asm volatile("" : "+r"(bt0), "+r"(bt1), "+r"(bw0), "+r"(bw1), "+f"(fsel));         // keep them in registers (no rematerialisation in the loop)
+    const uint32_t a_parkA = pinned_smem_addr(&s_q[warp][QROW * g + 2 * t]);
+    const uint32_t a_parkW = pinned_smem_addr(&s_q[warp][QW_OFF + QROW * g + 2 * (t & 1)]);
+    // column sums: lane (c, h) = (lane & 15, lane >> 4) adds rows h, h + 2, h + 4, h + 6 of column c (12 live columns)
+    const int red_c = lane & 15, red_h = lane >> 4;
+    const bool red_on = red_c < GS_REC_FLOATS;
+    const uint32_t a_col = pinned_smem_addr(&s_q[warp][red_c < 8 ? red_h * QROW + red_c : (red_on ? QW_OFF + red_h * QROW + red_c - 8 : 0)]);
+    const uint32_t a_out = pinned_smem_addr(&s_acc[warp][red_on ? red_c : 0]);
+    const bool red_tag = red_c == 5;                             // column 5 is identically zero: its slot carries the record index
+    const float4* __restrict__ my_acc = reinterpret_cast<const float4*>(s_acc[warp]);
+
+    for (;;) {
+        long long item = 0;
+        if (lane == 0) item = fetch_heavy<NWT>(p, &p.status->q_bwd_heavy);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item == ITEM_DONE) break;
+
+        const int sub = (int)(item & 7);
+        const TileCtx tc = tile_ctx(p, item >> 3);
+        const int bx0 = tc.tx0 + (sub & 1) * 8, by0 = tc.ty0 + (sub >> 1) * 8;      // origin of this warp's 8 x 8 block
+        const unsigned my_blocks = warp_blocks<PX>(sub);
+        const size_t vb = (size_t)tc.v * HW;
+        const float* __restrict__ bg = p.cams + (size_t)tc.v * GS_CAM_FLOATS + GS_CAM_BG;
+        const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+
+        const int px = bx0 + g;
+        const float pxf = (float)px;
+        float pyf[PX], T[PX], Q[PX], g0[PX], g1[PX], g2[PX], gd[PX], ga[PX];
+        uint32_t last[PX];
+        #pragma unroll
+        for (int k = 0; k < PX; k++) {
+            const int py = by0 + t + 4 * k;
+            pyf[k] = (float)py;
+            T[k] = 0.f; last[k] = 0u; g0[k] = g1[k] = g2[k] = gd[k] = ga[k] = 0.f;
+            if (px < p.W && py < p.H) {
+                const size_t pix = (size_t)py * p.W + px;
+                T[k] = p.final_T[vb + pix];
+                last[k] = p.n_contrib[vb + pix];
+                g0[k] = io.dL_dcolor[vb * 3 + pix]; g1[k] = io.dL_dcolor[vb * 3 + HW + pix]; g2[k] = io.dL_dcolor[vb * 3 + 2 * HW + pix];
+                if (io.dL_ddepth) gd[k] = io.dL_ddepth[vb + pix];
+                if (io.dL_dalpha) ga[k] = io.dL_dalpha[vb + pix];
+            }
+            Q[k] = T[k] * (b0 * g0[k] + b1 * g1[k] + b2 * g2[k]);                // T_final * (bg . dL/dC)
+        }
+        uint32_t m = max(last[0], last[1]);
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const int nmax = (int)min(m, (uint32_t)tc.n);           // deepest contributor of this warp's pixels
+        if (nmax == 0) continue;                                // warp-uniform
+
+        const int nchunks = (nmax + CHUNK - 1) / CHUNK;
+        const float4* __restrict__ src = p.sorted_rec + tc.start * 3;
+        float4* __restrict__ gbase = p.grad2d + (size_t)tc.v * p.N * 3;
+        const float fxc0 = (float)bx0 + 3.5f, fyc0 = (float)by0 + 3.5f;               // block centre
+        if (lane == 0) {
+            const int c = nchunks - 1;
+            const uint32_t bytes = (uint32_t)(nmax - c * CHUNK) * REC_BYTES;
+            mbar_expect_tx(&bar[0], bytes);
+            bulk_g2s(ring[0], src + (size_t)c * CHUNK * 3, bytes, &bar[0]);
+        }
+        for (int kc = 0; kc < nchunks; kc++) {
+            const int c = nchunks - 1 - kc, cur = kc & 1;
+            __syncwarp();                                       // every lane is done with ring[cur ^ 1] (walk and flush)
+            if (c > 0 && lane == 0) {
+                const uint32_t bytes = (uint32_t)CHUNK * REC_BYTES;              // every earlier chunk is full
+                mbar_expect_tx(&bar[cur ^ 1], bytes);
+                bulk_g2s(ring[cur ^ 1], src + (size_t)(c - 1) * CHUNK * 3, bytes, &bar[cur ^ 1]);
+            }
+            mbar_wait(&bar[cur], (phases >> cur) & 1u);
+            phases ^= 1u << cur;
+            const int cnt = min(nmax - c * CHUNK, CHUNK);
+            const float4* __restrict__ rec = ring[cur];
+            const uint32_t* __restrict__ recw = reinterpret_cast<const uint32_t*>(ring[cur]);
+            unsigned live = __ballot_sync(0xffffffffu, lane < cnt && ((recw[lane * 12 + 11] >> 24) & my_blocks) != 0u);
+            int nt = 0;                                         // warp-uniform: records reduced so far (rows of s_acc in use)
+            int lastc[PX];                                      // pixel k contributes to records j < lastc[k] of this chunk
+            #pragma unroll
+            for (int k = 0; k < PX; k++) lastc[k] = (int)last[k] - c * CHUNK;
+            while (live) {                                      // warp-uniform
+                const int j = msb_index(live);
+                live ^= 1u << j;
+                const float4 r0 = rec[j * 3], r1 = rec[j * 3 + 1];
+                const ColTerms ct = col_terms(r0.z, r0.w, r1.x, __fsub_rn(r0.x, pxf));
+                float pw[PX];
+                bool hit[PX], any = false;
+                #pragma unroll
+                for (int k = 0; k < PX; k++) {
+                    pw[k] = splat_power(ct, __fsub_rn(r0.y, pyf[k]));                   // same expression, same bits as the forward
+                    hit[k] = pw[k] >= r1.w && j < lastc[k];            // the (rare) power > 0 skip is tested on the blend path
+                    any = any || hit[k];
+                }
+                if (!__any_sync(0xffffffffu, any)) continue;
+                float tt[PX], wq[4];                            // tt = G dL/dalpha per pixel; wq = sum_k w (g_depth, g_r, g_g, g_b)
+                tt[0] = tt[1] = 0.f; wq[0] = wq[1] = wq[2] = wq[3] = 0.f;
+                const float4 r2 = rec[j * 3 + 2];
+                #pragma unroll
+                for (int k = 0; k < PX; k++) {
+                    if (hit[k]) {
+                        const float G = splat_exp(pw[k]);
+                        const float alpha = splat_alpha(r1.y, G);
+                        if (alpha >= GS_ALPHA_MIN && pw[k] <= 0.0f) {
+                            // T_i = T_{i+1} / (1 - alpha_i) with a Newton-refined reciprocal (see blend_bwd_kernel)
+                            const float om = __fsub_rn(1.0f, alpha);             // in [0.01, 1]
+                            float ra;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(om));
+                            ra = __fmaf_rn(__fmaf_rn(-om, ra, 1.0f), ra, ra);
+                            const float Tk = __fmul_rn(T[k], ra);
+                            const float w = __fmul_rn(alpha, Tk);
+                            const float Pk = __fmaf_rn(g0[k], r2.x, __fmaf_rn(g1[k], r2.y, __fmaf_rn(g2[k], r2.z, __fmaf_rn(gd[k], r1.z, ga[k]))));
+                            const float dLda = Tk * Pk - ra * Q[k];
+                            Q[k] = __fmaf_rn(w, Pk, Q[k]);
+                            tt[k] = G * dLda;
+                            wq[0] = __fmaf_rn(w, gd[k], wq[0]);
+                            wq[1] = __fmaf_rn(w, g0[k], wq[1]); wq[2] = __fmaf_rn(w, g1[k], wq[2]); wq[3] = __fmaf_rn(w, g2[k], wq[3]);
+                            T[k] = Tk;
+                        }
+                    }
+                }
+                {
+                    unsigned th[PX], tl[PX], wh[4], wl[4];
+                    split_tf32(tt[0], th[0], tl[0]); split_tf32(tt[1], th[1], tl[1]);
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) split_tf32(wq[i], wh[i], wl[i]);
+                    // geometric moments: A = rows (x = g | hi, x = g | lo), k = y: a0 = hi(y = t), a1 = lo(y = t), a2 = hi(y = t + 4), a3 = lo(y = t + 4)
+                    float dt[4] = {0.f, 0.f, 0.f, 0.f}, dw[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_tf32_16x8x8(dt, th[0], tl[0], th[1], tl[1], bt0, bt1);
+                    // colour / depth moments: a0 = wq0 (row g, k < 4), a1 = wq2 (row g + 8, k < 4), a2 = wq1 (row g, k >= 4), a3 = wq3 (row g + 8, k >= 4)
+                    mma_tf32_16x8x8(dw, wl[0], wl[2], wl[1], wl[3], bw0, bw1);
+                    mma_tf32_16x8x8(dw, wh[0], wh[2], wh[1], wh[3], bw0, bw1);
+                    // lane t of quad g now holds (S_{col 2t}, S_{col 2t+1}) of column x = g (hi in c0/c1, lo in c2/c3) and, for t < 2, the
+                    // quad sums (wq0, wq2) [t = 0] or (wq1, wq3) [t = 1] in dw[0], dw[2]
+                    sts_v2(a_parkA, fsel * (dt[0] + dt[2]), fsel * (dt[1] + dt[3]));
+                    if (t < 2) sts_v2(a_parkW, dw[0], dw[2]);
+                    __syncwarp();
+                    constexpr int RS = 2 * QROW * 4;                     // byte stride of two rows
+                    float acc = (lds_f32<0 * RS>(a_col) + lds_f32<1 * RS>(a_col)) + (lds_f32<2 * RS>(a_col) + lds_f32<3 * RS>(a_col));
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                    if (red_h == 0 && red_on) sts_f32(a_out + (uint32_t)nt * (GS_REC_FLOATS * 4), red_tag ? __int_as_float(j) : acc);
+                    nt++;
+                    __syncwarp();
+                }
+            }
+            // flush the chunk.  s_acc row r (r-th reduced record, compact) = (M1, My, Mx, Mxy | Myy, [record index], Mxx, 0 |
+            // sum w g_d, sum w g_g, sum w g_r, sum w g_b): moments of tt about the block centre.  Re-centre on the splat (dx = ex - x',
+            // dy = ey - y'), then gradients of the 2-D record (pix.x, pix.y, conic A, B | C, opacity, depth, _ | rgb), conic B being
+            // the true (not halved) derivative; one 16-byte RED per (record, part).
+            __syncwarp();
+            for (int u = lane; u < nt * 3; u += 32) {
+                const int r = u / 3, part = u - r * 3;
+                const float4 m1 = my_acc[r * 3 + 1];
+                const int j = __float_as_int(m1.y);
+                const float4 q0 = rec[j * 3], q1 = rec[j * 3 + 1];
+                const float o = q1.y;
+                float4 a;
+                if (part == 2) {
+                    const float4 mw = my_acc[r * 3 + 2];
+                    a = make_float4(mw.z, mw.y, mw.w, 0.f);
+                } else {
+                    const float4 m0 = my_acc[r * 3];
+                    const float ex = __fsub_rn(q0.x, fxc0), ey = __fsub_rn(q0.y, fyc0);
+                    const float M1 = m0.x, My = m0.y, Mx = m0.z, Mxy = m0.w, Myy = m1.x, Mxx = m1.z;
+                    const float Sx = __fmaf_rn(ex, M1, -Mx), Sy = __fmaf_rn(ey, M1, -My);      // sum tt dx, sum tt dy
+                    if (part == 0) {
+                        const float Sxx = __fmaf_rn(ex, Sx - Mx, Mxx);                          // ex^2 M1 - 2 ex Mx + Mxx
+                        const float Sxy = __fmaf_rn(ex, Sy, __fmaf_rn(-ey, Mx, Mxy));            // ex ey M1 - ex My - ey Mx + Mxy
+                        a = make_float4(-o * (q0.z * Sx + q0.w * Sy), -o * (q1.x * Sy + q0.w * Sx), -0.5f * o * Sxx, -o * Sxy);
+                    } else {
+                        const float Syy = __fmaf_rn(ey, Sy - My, Myy);
+                        a = make_float4(-0.5f * o * Syy, M1, my_acc[r * 3 + 2].x, 0.f);
+                    }
+                }
                 const int id = __float_as_int(rec[j * 3 + 2].w) & 0x00ffffff;
                 red_add_v4(gbase + (size_t)id * 3 + part, a);
             }
@@ -596,7 +874,16 @@ void gs_launch_blend_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms,
 {
     switch (pick_px(p)) {
         case 1: launch_bwd<1>(p, io, num_sms, s); break;
-        case 2: launch_bwd<2>(p, io, num_sms, s); break;
+        case 2: {
+#if GS_BWD_MMA
+            static thread_local int grid = 0, grid_sms = 0;
+            if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_bwd_mma_kernel, WPC * 32, num_sms, 4); grid_sms = num_sms; }
+            blend_bwd_mma_kernel<<<grid, WPC * 32, 0, s>>>(p, io);
+#else
+            launch_bwd<2>(p, io, num_sms, s);
+#endif
+            break;
+        }
         default: launch_bwd<4>(p, io, num_sms, s); break;
     }
 }
