@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "upstream_style"])
+    ap.add_argument("--workloads", default="all", help="comma list of config2,geometry,texture,bake ('all' = every one at N = 1, "
+                    "config2 only at N > 1); the headline metric is always config2, the others are extra keys of the same line")
     ap.add_argument("--views", type=int, default=24)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
@@ -169,6 +171,125 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def measure_e2e(a, dev, world, rank, host, cam_groups, gimgs, H, W, use_sh, n_grad):
+    """End-to-end steps through the plugin.  Per step: ONE host->device copy of the packed parameters (rank 0; the other ranks
+    receive them by an NCCL broadcast over NVLink instead of each pulling 14 MB through its own PCIe link), render_views +
+    autograd backward of the local views, gradients reduced to rank 0 (one NCCL reduce) and ONE device->host copy of the flat
+    gradient buffer.  Two modes are timed: 'serial' (copy in, compute, copy out, wait -- nothing overlaps) and 'pipelined'
+    (double-buffered: the upload of step k+1 and the download of step k-1 run on side streams beside the kernels of step k; the
+    host waits for the gradients of step k-1 before it issues step k+1, so the run-ahead is bounded to one step)."""
+    import torch
+    import torch.distributed as dist
+    from topo4d_b200.rasterizer import render_views
+
+    names = [k for k in ("means3D", "shs", "colors_precomp", "opacities", "scales", "rotations") if k in host]
+    offs, o = {}, 0
+    for k in names:
+        offs[k] = (o, host[k].numel(), tuple(host[k].shape))
+        o += (host[k].numel() + 3) // 4 * 4                      # 16-byte aligned segments (float4 loads in the kernels)
+    n_in = o
+    host_in = torch.empty(n_in, dtype=torch.float32).pin_memory()
+    for k in names:
+        s0, n, _ = offs[k]
+        host_in[s0:s0 + n].copy_(host[k].reshape(-1))
+    dev_in = [torch.empty(n_in, dtype=torch.float32, device=dev) for _ in range(2)]
+    dev_out = [torch.empty(n_grad, dtype=torch.float32, device=dev) for _ in range(2)]
+    host_out = [torch.empty(n_grad, dtype=torch.float32).pin_memory() for _ in range(2)]
+    part = [torch.empty(n_grad, dtype=torch.float32, device=dev) for _ in range(len(cam_groups) - 1)]
+    main = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    mk = lambda: [torch.cuda.Event(), torch.cuda.Event()]
+    ev_in, ev_done, ev_out = mk(), mk(), mk()
+
+    def upload(k, stream):
+        b = k % 2
+        with torch.cuda.stream(stream):
+            stream.wait_event(ev_done[b])                          # the kernels of step k-2 have finished reading dev_in[b]
+            if rank == 0:
+                dev_in[b].copy_(host_in, non_blocking=True)
+            if world > 1:
+                dist.broadcast(dev_in[b], src=0)
+            ev_in[b].record(stream)
+
+    def compute(k):
+        b = k % 2
+        main.wait_event(ev_in[b])
+        main.wait_event(ev_out[b])                                 # dev_out[b] of step k-2 has been downloaded
+        leaf = {}
+        for name in names:
+            s0, n, shp = offs[name]
+            leaf[name] = dev_in[b][s0:s0 + n].view(shp).detach().requires_grad_(True)
+        for g in range(len(cam_groups)):
+            buf = dev_out[b] if g == 0 else part[g - 1]
+            color, _, depth, alpha = render_views(cam_groups[g], H, W, leaf["means3D"], None, leaf["opacities"], shs=leaf.get("shs"),
+                                                  colors_precomp=leaf.get("colors_precomp"), scales=leaf["scales"],
+                                                  rotations=leaf["rotations"], sh_degree=a.sh_degree if use_sh else 0, grad_buffer=buf)
+            torch.autograd.backward((color, depth, alpha), gimgs[g])
+            if g > 0:
+                dev_out[b].add_(buf)
+        ev_done[b].record(main)
+
+    def download(k, stream):
+        b = k % 2
+        with torch.cuda.stream(stream):
+            stream.wait_event(ev_done[b])
+            if world > 1:
+                dist.reduce(dev_out[b], dst=0)
+            if rank == 0:
+                host_out[b].copy_(dev_out[b], non_blocking=True)
+            ev_out[b].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(pipelined):
+        os.environ["TOPO4D_B200_SYNC"] = "0"                        # asynchronous forward: the status block is checked one call later
+        for e in ev_in + ev_done + ev_out:
+            e.record(main)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(main)
+        if pipelined:
+            upload(0, s_in)
+            for k in range(a.steps):
+                if k + 1 < a.steps:
+                    upload(k + 1, s_in)
+                compute(k)
+                download(k, s_out)
+                if k > 0:
+                    ev_out[(k - 1) % 2].synchronize()             # the host now holds the gradients of step k-1
+            main.wait_stream(s_out)
+        else:
+            for k in range(a.steps):
+                upload(k, main)
+                compute(k)
+                download(k, main)
+                main.synchronize()                                 # the caller needs the gradients on the host before the next step
+        f1.record(main)
+        barrier()
+        ms = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    out = {}
+    for mode in (False, True):
+        timed(mode)                                                # warm-up of this mode (allocations, autograd graph, NCCL channels)
+        ms = timed(mode)
+        out["pipelined" if mode else "serial"] = a.steps * a.views * H * W / 1e6 / (ms / 1e3)
+    os.environ["TOPO4D_B200_SYNC"] = "1"
+    from topo4d_b200 import rasterizer
+    rasterizer._check_pending()
+    return {"value": out["pipelined"], "unit": UNIT, "h2d_bytes_per_step": int(n_in * 4), "d2h_bytes_per_step": int(n_grad * 4),
+            "serial_value": out["serial"],
+            "api": "topo4d_b200.rasterizer.render_views (GaussianRasterizer over V cameras) + torch.autograd.backward",
+            "how": "pipelined: double-buffered, H2D of step k+1 / D2H of step k-1 on side streams beside the kernels of step k, host waits "
+                   "for step k-1's gradients before issuing step k+1; serial_value: copy in, compute, copy out, wait, nothing overlaps"
+                   + ("; N > 1: rank 0 uploads once, NCCL broadcast; NCCL reduce to rank 0, one download" if world > 1 else "")}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -281,30 +402,11 @@ def run_ours(a):
     stage_share = {k: float(np.sum([x.elapsed_time(y) for x, y in v])) * (a.steps / max(sampled, 1)) / e0.elapsed_time(e1)
                    for k, v in ev.items()}
 
-    # ---- e2e: same step through the public API with HOST buffers: H2D of the parameters, D2H of the gradients ----
+    # ---- e2e: the same step through the reference-facing plugin (render_views = GaussianRasterizer over V cameras, autograd
+    # backward) with HOST buffers: the parameters leave pinned host memory and the gradients return to it inside the timed region.
     e2e = None
     if not a.no_e2e:
-        grads_host = torch.empty(flat.numel(), dtype=torch.float32).pin_memory()
-        h2d = sum(v.numel() * 4 for v in host.values())
-        d2h = grads_host.numel() * 4
-        for _ in range(2):
-            p = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            grads_host.copy_(step(p), non_blocking=True)
-            torch.cuda.synchronize()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(a.steps):
-            p = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            grads_host.copy_(step(p), non_blocking=True)
-            torch.cuda.current_stream().synchronize()          # the caller needs the gradients on the host every step
-        f1.record()
-        barrier()
-        ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e = {"value": a.steps * a.views * H * W / 1e6 / (float(ms2.item()) / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        e2e = measure_e2e(a, dev, world, rank, host, cam_groups, gimgs, H, W, use_sh, flat.numel())
     clocks = sampler.stop() if sampler else None
 
     # ---- on-hardware check of the multi-GPU result: the all-reduced flat buffer of the view-parallel step must equal the
@@ -362,14 +464,20 @@ def run_ours(a):
                 bw[k] = b / (stage_ms[k] * 1e-3) / 1e9
         dom = max(("blend_fwd", "blend_bwd"), key=lambda k: stage_ms.get(k, 0.0))
         # measured DRAM traffic of the same kernel from the committed ncu capture (only valid for the same workload)
-        traffic, traffic_src = None, None
+        traffic, traffic_src = None, "no ncu capture of the current kernel sources under profiles/ (older *_traffic.json ignored)"
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01i_traffic.json")))
-            w = tj["workload"]
-            if (w["views_per_launch"], w["width"], w["height"], w["gaussians"], w["sh_degree"], w["opacity"]) == \
-                    (vpl, a.width, a.height, a.gaussians, a.sh_degree, a.opacity):
-                traffic = tj["dram_bytes_per_launch"].get(dom + "_kernel")
-                traffic_src = tj["source"]
+            import glob
+            from topo4d_b200 import build as _b
+            cur = _b._source_hash()
+            for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+                tj = json.load(open(f))
+                w = tj["workload"]
+                if tj.get("kernel_src_hash") == cur and \
+                        (w["views_per_launch"], w["width"], w["height"], w["gaussians"], w["sh_degree"], w["opacity"]) == \
+                        (vpl, a.width, a.height, a.gaussians, a.sh_degree, a.opacity):
+                    traffic = tj["dram_bytes_per_launch"].get(dom + "_kernel")
+                    traffic_src = tj["source"]
+                    break
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": bw.get(dom), "peak": peak, "unit": "GB/s",
@@ -396,6 +504,26 @@ def run_ours(a):
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof}
         if verify is not None:
             line["verify"] = verify
+        # pairs / covered-pixel rates beside the headline (94.6 % of this workload's pixels are background fill)
+        if stats["covered_pixels"]:
+            sec = ms_total / a.steps / 1e3
+            line["rates"] = {"covered_mpix_s": stats["covered_pixels"] * world / 1e6 / sec,
+                             "instances_m_s": stats["num_rendered"] * world / 1e6 / sec,
+                             "tested_pixel_gaussian_pairs_g_s": stats["num_rendered"] * world * 256 / 1e9 / sec,
+                             "note": "rank-0 counts x ranks; pairs = (tile, Gaussian) instances x 256 pixels"}
+        # the reference's own regimes and config 4, as extra keys of the same line (N = 1 only)
+        wl = [w for w in ("geometry", "texture", "bake") if a.workloads == "all" or w in a.workloads.split(",")]
+        if world == 1 and wl:
+            del t, gimgs, flat_bufs
+            torch.cuda.empty_cache()
+            from tools import workloads as W_
+            line["workloads"] = {}
+            for w in wl:
+                try:
+                    line["workloads"][w] = getattr(W_, w)()
+                except Exception as e:  # noqa: BLE001  (a side workload never takes the headline down)
+                    line["workloads"][w] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
         if world == 1 and not a.no_cpu_baseline:
             nv = max(1, min(a.cpu_sample_views, a.views))
             from oracle import gs_oracle

@@ -15,6 +15,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
+def _src_hash():
+    """Content hash of the kernel sources the capture was taken with: bench.py only quotes a traffic file whose hash equals
+    the current tree's, so the figure cannot silently go stale when a kernel changes."""
+    sys.path.insert(0, ROOT)
+    from topo4d_b200 import build
+    return build._source_hash()
+
+
 def main():
     tag = sys.argv[1]
     src, dst = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
@@ -32,12 +40,12 @@ def main():
         ir, iw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
         traffic = {}
         for r in rows[2:]:
-            name = r[h.index("Kernel Name")].split("(")[0].split("::")[-1].split("<")[0]
+            name = r[h.index("Kernel Name")].split("(")[0].split("::")[-1].split("<")[0].replace("_mma_kernel", "_kernel")
             traffic.setdefault(name, int(float(r[ir]) * UNIT[u[ir]] + float(r[iw]) * UNIT[u[iw]]))
         json.dump({"source": f"ncu --set full --clock-control none capture summarised in profiles/{tag}_all_kernels_ncu.txt "
                              f"(gpurun_out/{tag}_all.ncu-rep); command: python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline",
                    "workload": {"views_per_launch": 24, "width": 1920, "height": 1080, "gaussians": 60000, "sh_degree": 3, "opacity": "topo4d"},
-                   "dram_bytes_per_launch": traffic}, open(os.path.join(dst, f"{tag}_traffic.json"), "w"), indent=1)
+                   "kernel_src_hash": _src_hash(), "dram_bytes_per_launch": traffic}, open(os.path.join(dst, f"{tag}_traffic.json"), "w"), indent=1)
         for k in ("fwd", "bwd"):
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot.py"), rep, "blend_" + k, "1.0"],
                                  capture_output=True, text=True).stdout.splitlines()
@@ -56,7 +64,7 @@ def main():
         tot = sum(v for _, v in step)
         print("launch list, one step (us):", {k: round(v, 1) for k, v in step}, "sum", round(tot, 1))
         print("shares (%):", {k: round(100 * v / tot, 1) for k, v in step})
-    print(f"remember: sed -i 's/r0.._traffic.json/{tag}_traffic.json/' bench.py")
+    print("bench.py picks the newest profiles/*_traffic.json whose kernel_src_hash matches the tree")
 
 
 if __name__ == "__main__":

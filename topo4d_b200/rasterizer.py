@@ -103,7 +103,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                cameras, image_height, image_width, sh_degree, scale_modifier, debug):
+                cameras, image_height, image_width, sh_degree, scale_modifier, debug, grad_buffer):
         capturing = means3D.is_cuda and torch.cuda.is_current_stream_capturing()
         sync = _sync_mode() and not capturing
         if not sync and not capturing:
@@ -123,6 +123,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                                                         sh_degree=sh_degree, scale_modifier=scale_modifier), "forward")
             raise
         ctx.debug = bool(debug)
+        ctx.grad_buffer = grad_buffer          # optional caller-owned flat fp32 buffer the backward writes its gradients into
         if capturing:
             _CAPTURE_LOG.append(state)
         elif not sync:
@@ -143,7 +144,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         state = ctx.state
         ctx.saved_tensors                      # version-counter check of every input the kernels are about to re-read
         try:
-            g = engine.backward(state, grad_color, grad_depth, grad_alpha)
+            g = engine.backward(state, grad_color, grad_depth, grad_alpha, flat=ctx.grad_buffer)
         except Exception:
             if ctx.debug:
                 _dump_snapshot("snapshot_bw.dump", dict(zip(("means3D", "opacities", "sh", "colors_precomp", "scales", "rotations",
@@ -155,7 +156,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = lambda t, shp: None if (t is None or shp is None) else t.reshape(shp)
         return (rs(g.means3D, s[0]), rs(g.means2D, s[1]), rs(g.shs, s[2]), rs(g.colors_precomp, s[3]),
                 rs(g.opacities, s[4]), rs(g.scales, s[5]), rs(g.rotations, s[6]), rs(g.cov3D_precomp, s[7]),
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 def _none_if_empty(t):
@@ -164,13 +165,19 @@ def _none_if_empty(t):
 
 def render_views(cameras: torch.Tensor, image_height: int, image_width: int, means3D, means2D, opacities, *,
                  shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, sh_degree=0,
-                 scale_modifier=1.0, debug=False):
+                 scale_modifier=1.0, debug=False, grad_buffer=None):
     """All V views of `cameras` [V,48] in one pass; returns (color[V,3,H,W], radii[V,N], depth[V,1,H,W],
-    alpha[V,1,H,W]); gradients are summed over the views."""
+    alpha[V,1,H,W]); gradients are summed over the views.
+
+    grad_buffer: optional contiguous fp32 CUDA tensor of at least ``engine.flat_layout(...)[1]`` elements.  The backward
+    then writes every gradient into it (the ``.grad`` tensors autograd hands out are views of it, layout
+    ``engine.flat_layout``), so a view-parallel caller can exchange or download ALL gradients of the step with one
+    collective / one copy instead of gathering six tensors."""
     if means2D is None:
         means2D = torch.zeros_like(means3D)
     return _RasterizeGaussians.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                     cov3D_precomp, cameras, image_height, image_width, sh_degree, scale_modifier, debug)
+                                     cov3D_precomp, cameras, image_height, image_width, sh_degree, scale_modifier, debug,
+                                     grad_buffer)
 
 
 class GaussianRasterizer(nn.Module):
@@ -191,5 +198,5 @@ class GaussianRasterizer(nn.Module):
         cam = pack_settings(rs).reshape(1, GS_CAM_FLOATS)
         color, radii, depth, alpha = _RasterizeGaussians.apply(
             means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cam,
-            int(rs.image_height), int(rs.image_width), int(rs.sh_degree), float(rs.scale_modifier), bool(rs.debug))
+            int(rs.image_height), int(rs.image_width), int(rs.sh_degree), float(rs.scale_modifier), bool(rs.debug), None)
         return color[0], radii[0], depth[0], alpha[0]

@@ -183,3 +183,27 @@ def uv_grid_mesh(grid: int = 245, res: int = 8192, seed: int = 0, jitter: float 
         tris = np.concatenate([tris, nv + np.arange(12).reshape(4, 3)], 0)
     colors = rng.uniform(0, 1, (verts.shape[0], 3))
     return verts.astype(np.float64), tris.astype(np.int64), colors.astype(np.float64)
+
+
+def dense_head_scene(n: int = 4_000_000, seed: int = 0, opacity: float = 1.0):
+    """Texture-stage stand-in (4-5 M UV-densified Gaussians, colours optimised against ~4096x3000 photos,
+    helpers.py:608-609, train.py:715-743): n points on the same head ellipsoid as :func:`head_scene`, isotropic scale = half
+    the local point spacing (analytic: sqrt(surface area per point) -- a k-d tree over millions of points would dominate the
+    set-up), rotation from the normal, ``colors_precomp`` colours (the reference never uses SH, helpers.py:82,94,105)."""
+    rng = np.random.default_rng(seed)
+    i = np.arange(n, dtype=np.float64) + 0.5
+    phi = np.arccos(1 - 2 * i / n)
+    theta = math.pi * (1 + 5 ** 0.5) * i
+    d = np.stack([np.cos(theta) * np.sin(phi), np.cos(phi), np.sin(theta) * np.sin(phi)], 1)
+    axes = np.array([0.09, 0.12, 0.10])
+    pts = d * axes
+    nrm = d / axes
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    # area element of the ellipsoid per unit-sphere area: |axes-scaled normal| factor
+    stretch = np.linalg.norm(d / axes, axis=1) * axes.prod()
+    spacing = np.sqrt(4 * math.pi * stretch / n)
+    sc = 0.5 * spacing * np.exp(rng.normal(0, 0.1, n))
+    albedo = 0.5 + 0.3 * np.stack([np.sin(70 * d[:, 0] + 1.0), np.sin(50 * d[:, 1] + 2.0), np.sin(60 * d[:, 2] + 3.0)], 1)
+    out = dict(means3D=pts, scales=np.repeat(sc[:, None], 3, 1), rotations=_quat_from_normals(nrm),
+               opacities=np.full((n, 1), opacity), colors_precomp=albedo)
+    return {k: np.ascontiguousarray(v, np.float32) for k, v in out.items()}
