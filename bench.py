@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--ref-views-per-step", type=int, default=4, help="views per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-upstream-style", action="store_true", help="skip the upstream-style CUDA denominator (ours arm, N = 1)")
     ap.add_argument("--blend-px", type=int, default=0, help="force the blend kernels' pixels per thread (0 = auto)")
     ap.add_argument("--verify", action="store_true", help="also at N = 1: compare the step's gradient buffer with an independent "
                     "single-launch pass over all views (always done when N > 1)")
@@ -171,6 +172,71 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# upstream-style CUDA arm (tools/upstream_style): the same workload through a plain restatement of the reference
+# rasterizer's published GPU mapping -- the same-box denominator of BASELINE.json's ">= 10x the reference rasterizer"
+# ------------------------------------------------------------------------------------------------
+def upstream_style_steps(a, dev, t, cam_all, gimgs_per_view, steps, warmup=1):
+    """ms per step (all a.views views, one view per call like the reference renders) and instances per step."""
+    import torch
+    from tools import upstream_style as US
+    from topo4d_b200 import engine
+    H, W = a.height, a.width
+    use_sh = "shs" in t
+    M = int(t["shs"].shape[1]) if use_sh else 0
+    _, n_flat = engine.flat_layout(a.gaussians, M, use_sh, False)
+    total, one = torch.zeros(n_flat, device=dev), torch.empty(n_flat, device=dev)
+    cams = [cam_all[i:i + 1].contiguous() for i in range(a.views)]
+    rendered = 0
+
+    def step():
+        nonlocal rendered
+        total.zero_()
+        rendered = 0
+        for i in range(a.views):
+            color, radii, depth, alpha, v = US.forward(t, cams[i], H, W, a.sh_degree if use_sh else 0)
+            rendered += US.num_rendered()
+            US.backward(v, *gimgs_per_view(i), one)
+            total.add_(one)
+        return total
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, rendered, total
+
+
+def run_upstream_style(a):
+    import torch
+    from topo4d_b200 import engine
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    scene, cams = workload(a)
+    t = {k: torch.tensor(v, device=dev) for k, v in scene.items()}
+    cam_all = torch.tensor(engine.pack_cameras_numpy(cams, (0.0, 0.0, 0.0)), device=dev)
+    H, W = a.height, a.width
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    gC = torch.sign(torch.rand((a.views, 3, H, W), device=dev, generator=gen) - 0.5) / (3 * H * W)
+    gD = torch.full((a.views, 1, H, W), 0.1 / (H * W), device=dev)
+    gA = torch.full((a.views, 1, H, W), 0.1 / (H * W), device=dev)
+    ms, rendered, _ = upstream_style_steps(a, dev, t, cam_all, lambda i: (gC[i], gD[i], gA[i]), a.steps, max(a.warmup, 1))
+    value = a.views * H * W / 1e6 / (ms / 1e3)
+    line = {"impl": "upstream_style", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 1),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(a, {"num_rendered": rendered, "note": "upstream-style CUDA pipeline (tools/upstream_style/us_raster.cu): CUB scan + "
+                                      "host read of num_rendered, duplicateWithKeys, 64-bit CUB radix sort, 16x16 block per tile, per-thread global "
+                                      "atomics in the backward; preprocess forward/backward are this repository's kernels; one view per call"})}
+    print(json.dumps(line), flush=True)
+
+
 def measure_e2e(a, dev, world, rank, host, cam_groups, gimgs, H, W, use_sh, n_grad):
     """End-to-end steps through the plugin.  Per step: ONE host->device copy of the packed parameters (rank 0; the other ranks
     receive them by an NCCL broadcast over NVLink instead of each pulling 14 MB through its own PCIe link), render_views +
@@ -437,9 +503,11 @@ def run_ours(a):
         worst = torch.tensor([max(errs.values())], device=dev)
         if world > 1:
             dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-        verify = {"grad_relerr_vs_single_gpu": float(worst.item()), "per_tensor_rank0": errs, "tolerance": 1e-4,
+        verify = {"grad_relerr_vs_single_gpu": float(worst.item()), "per_tensor_rank0": errs, "tolerance": 5e-4,
                   "what": f"flat gradient buffer after the {world}-rank all-reduce vs one process rendering all {a.views} views "
-                          "(fp32 sums in a different order)"}
+                          "(two fp32 evaluations whose atomics and view sums run in different orders: the same noise as two runs of one "
+                          "configuration, tests/test_rasterizer_gpu.py::test_forward_is_deterministic_and_backward_close; the spec's bound "
+                          "against the oracle is 1e-3)"}
         del color, depth, alpha, st, gC, ref, got
 
     # overflow check after the timed region (capacity was fixed; the flag is sticky per workspace)
@@ -511,6 +579,24 @@ def run_ours(a):
                              "instances_m_s": stats["num_rendered"] * world / 1e6 / sec,
                              "tested_pixel_gaussian_pairs_g_s": stats["num_rendered"] * world * 256 / 1e9 / sec,
                              "note": "rank-0 counts x ranks; pairs = (tile, Gaussian) instances x 256 pixels"}
+        # same-box CUDA denominator: the upstream-style pipeline on the same workload and the same loss-gradient images
+        if world == 1 and not a.no_upstream_style:
+            try:
+                gC_, gD_, gA_ = gimgs[0]
+                us_ms, us_I, us_flat = upstream_style_steps(a, dev, t, cam_all, lambda i: (gC_[i], gD_[i], gA_[i]), steps=3, warmup=1)
+                ours_flat = step(t)
+                M_ = int(t["shs"].shape[1]) if use_sh else 0
+                va, vb = engine.flat_views(us_flat, a.gaussians, M_, use_sh, False), engine.flat_views(ours_flat, a.gaussians, M_, use_sh, False)
+                # relative L2 distance per tensor (two different fp32 algorithms, 24 views summed: an elementwise bound relative to a
+                # floor would only measure how the per-view rounding noise of both adds up on the near-zero entries)
+                agree = {k: float((va[k].double() - vb[k].double()).norm() / (vb[k].double().norm() + 1e-300)) for k in va}
+                line["upstream_style"] = {"value": a.views * H * W / 1e6 / (us_ms / 1e3), "unit": UNIT, "ms_per_step": us_ms, "steps": 3,
+                                          "num_rendered": us_I, "grad_rel_l2_vs_ours": agree,
+                                          "what": "tools/upstream_style: CUB scan + host sync, duplicateWithKeys, 64-bit CUB radix sort, 16x16 block "
+                                                  "per tile, per-thread atomicAdd backward; one view per call; preprocess fwd/bwd are ours"}
+                line["vs_upstream_style"] = value / line["upstream_style"]["value"]
+            except Exception as e:  # noqa: BLE001
+                line["upstream_style"] = {"error": repr(e)[:300]}
         # the reference's own regimes and config 4, as extra keys of the same line (N = 1 only)
         wl = [w for w in ("geometry", "texture", "bake") if a.workloads == "all" or w in a.workloads.split(",")]
         if world == 1 and wl:
@@ -540,6 +626,8 @@ def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "upstream_style":
+        run_upstream_style(a)
     else:
         run_ours(a)
 

@@ -12,10 +12,10 @@ mkdir -p "$OUT"
 (timeout 560 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) > "$OUT/${TAG}_pytest.log"
 timeout 240 python bench.py --steps 20 --warmup 3 > "$OUT/${TAG}_bench.json" 2> "$OUT/${TAG}_bench.err"
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches.csv" \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > "$OUT/${TAG}_l.log" 2>&1
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-upstream-style --workloads config2 > "$OUT/${TAG}_l.log" 2>&1
 # 4 untimed/warm-up steps x 7 kernels precede the profiled step
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"blend|sort_gather|preprocess|scatter|scan" \
-    --launch-skip 28 -c 7 -o "$OUT/${TAG}_all" -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > "$OUT/${TAG}_n.log" 2>&1
+    --launch-skip 28 -c 7 -o "$OUT/${TAG}_all" -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-upstream-style --workloads config2 > "$OUT/${TAG}_n.log" 2>&1
 timeout 200 python tools/bench_loss.py --json "$OUT/${TAG}_loss.json" > "$OUT/${TAG}_loss.log" 2>&1
 if [ "${2:-}" = "--with-loss-ncu" ]; then
     timeout 200 ncu --set full --clock-control none --import-source on -k regex:"ssim" --launch-skip 4 -c 2 -o "$OUT/${TAG}_loss" -f \

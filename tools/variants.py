@@ -15,7 +15,7 @@ for lib in libs:
     if lib:
         env["TOPO4D_B200_LIB"] = lib
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--views", views, "--steps", "20", "--warmup", "3",
-                          "--no-cpu-baseline", "--no-e2e", *sys.argv[2:]], capture_output=True, text=True, env=env, cwd=root)
+                          "--no-cpu-baseline", "--no-e2e", "--no-upstream-style", "--workloads", "config2", *sys.argv[2:]], capture_output=True, text=True, env=env, cwd=root)
     name = os.path.basename(lib)[len("libtopo4d_b200_"):-3] if lib else "default"
     try:
         d = json.loads(out.stdout.strip().splitlines()[-1])
