@@ -59,6 +59,11 @@ typedef void* gs_stream_t;          /* a cudaStream_t */
 #define GS_CAM_TANFOVX  38
 #define GS_CAM_TANFOVY  39          /* 40..47 reserved, must be 0 */
 
+#define GS_HINT_UNKNOWN      0
+#define GS_HINT_SHORT_LISTS  1
+#define GS_HINT_LONG_LISTS   2
+#define GS_HINT_SORT_MASK    3
+
 /* ---- problem description shared by forward and backward ---- */
 typedef struct GsProblem {
     int32_t N;                      /* Gaussians                                              */
@@ -72,7 +77,10 @@ typedef struct GsProblem {
                                        tiles: fewest instructions), 2 or 1 (few tiles: more warps per tile,
                                        lower latency); 0 or any other value = library default (4).  Never
                                        changes results.                                                   */
-    int32_t reserved0;              /* must be 0 */
+    int32_t hints;                  /* tuning hints, never change results.  Bits 0-1, per-tile list lengths the caller expects (from
+                                       GsStatus.max_tile_instances of an earlier call of the same shape): GS_HINT_UNKNOWN (0),
+                                       GS_HINT_SHORT_LISTS (no list longer than 2048: skip the long-list sort kernel),
+                                       GS_HINT_LONG_LISTS.  Other bits must be 0.                                      */
     int64_t cap_instances;          /* capacity (tile,Gaussian) instances of the workspace    */
     /* inputs, DEVICE pointers, fp32, contiguous.  Exactly one of shs|colors_precomp and
        exactly one of (scales,rotations)|cov3D_precomp must be non-NULL. */

@@ -11,6 +11,7 @@ import os
 from . import build as _build
 
 GS_CAM_FLOATS = 48
+GS_HINT_UNKNOWN, GS_HINT_SHORT_LISTS, GS_HINT_LONG_LISTS = 0, 1, 2
 GS_FWD_PREPROCESS, GS_FWD_SCATTER, GS_FWD_SORT, GS_FWD_BLEND, GS_FWD_ALL = 1, 2, 4, 8, 15
 GS_BWD_BLEND, GS_BWD_PREPROCESS, GS_BWD_ALL = 1, 2, 3
 GS_OK, GS_E_BAD_ARGS, GS_E_WORKSPACE_SMALL, GS_E_CUDA, GS_E_OVERFLOW, GS_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
@@ -21,7 +22,7 @@ _vp = C.c_void_p
 class GsProblem(C.Structure):
     _fields_ = [("N", C.c_int32), ("V", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32), ("scale_modifier", C.c_float),
-                ("debug", C.c_int32), ("blend_px", C.c_int32), ("reserved0", C.c_int32), ("cap_instances", C.c_int64),
+                ("debug", C.c_int32), ("blend_px", C.c_int32), ("hints", C.c_int32), ("cap_instances", C.c_int64),
                 ("means3D", _vp), ("shs", _vp), ("colors_precomp", _vp), ("opacities", _vp), ("scales", _vp),
                 ("rotations", _vp), ("cov3D_precomp", _vp), ("cameras", _vp),
                 ("workspace", _vp), ("workspace_bytes", C.c_size_t)]

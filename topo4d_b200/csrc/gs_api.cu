@@ -80,6 +80,7 @@ static GsParams make_params(const GsProblem* p, const GsLayout& L)
     q.grad2d = (float4*)(ws + L.off_grad2d);
     q.scan_blocks = L.scan_blocks;
     q.blend_px = p->blend_px;
+    q.sort_long = (p->hints & GS_HINT_SORT_MASK) != GS_HINT_SHORT_LISTS;       // unknown -> run the long-list kernel too
     return q;
 }
 

@@ -55,12 +55,12 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float* b, fl
     }
 }
 
-template <int K>   // K = (deg+1)^2 active SH coefficients, 0 = colors_precomp
+template <int K, int LPG>   // K = (deg+1)^2 active SH coefficients, 0 = colors_precomp
 __global__ void __launch_bounds__(128, 3)
 preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
 {
     const int t_global = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i_raw = t_global >> 2, vq = t_global & 3;     // Gaussian, view sub-lane
+    const int i_raw = t_global / LPG, vq = t_global % LPG;  // Gaussian, view sub-lane (LPG lanes share a Gaussian's views: 4, or 1 when V <= 2)
     const bool act = i_raw < p.N;                            // inactive lanes still take part in the shuffles
     const int i = act ? i_raw : 0;
     const float px = p.means3D[3 * i], py = p.means3D[3 * i + 1], pz = p.means3D[3 * i + 2];
@@ -100,7 +100,7 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
     #pragma unroll
     for (int k = 0; k < KK * 3; k++) gsh[k] = 0.f;
 
-    for (int v = vq; v < p.V && act; v += 4) {
+    for (int v = vq; v < p.V && act; v += LPG) {
         const size_t gid = (size_t)v * p.N + i;
         if (io.radii[gid] <= 0) continue;
         const float* __restrict__ cam = p.cams + (size_t)v * GS_CAM_FLOATS;
@@ -223,7 +223,7 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
 
     // combine the four view sub-lanes (lanes 4j..4j+3 of a warp), then lane 0 of the quad writes
     #pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
+    for (int o = 1; o < LPG; o <<= 1) {
         #pragma unroll
         for (int k = 0; k < 3; k++) { gm[k] += __shfl_xor_sync(0xffffffffu, gm[k], o); gcol[k] += __shfl_xor_sync(0xffffffffu, gcol[k], o); }
         gm2[0] += __shfl_xor_sync(0xffffffffu, gm2[0], o); gm2[1] += __shfl_xor_sync(0xffffffffu, gm2[1], o);
@@ -279,15 +279,23 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
 
 }  // namespace
 
+template <int LPG>
+static void launch_pbwd(const GsParams& p, const GsBackwardIO& io, cudaStream_t s)
+{
+    const int threads = 128, blocks = (int)(((long long)p.N * LPG + threads - 1) / threads);
+    if (!p.shs) { preprocess_bwd_kernel<0, LPG><<<blocks, threads, 0, s>>>(p, io); return; }
+    switch (p.deg) {
+        case 0: preprocess_bwd_kernel<1, LPG><<<blocks, threads, 0, s>>>(p, io); break;
+        case 1: preprocess_bwd_kernel<4, LPG><<<blocks, threads, 0, s>>>(p, io); break;
+        case 2: preprocess_bwd_kernel<9, LPG><<<blocks, threads, 0, s>>>(p, io); break;
+        default: preprocess_bwd_kernel<16, LPG><<<blocks, threads, 0, s>>>(p, io); break;
+    }
+}
+
 void gs_launch_preprocess_bwd(const GsParams& p, const GsBackwardIO& io, cudaStream_t s)
 {
     if (p.N == 0) return;
-    const int threads = 128, blocks = (int)(((long long)p.N * 4 + threads - 1) / threads);
-    if (!p.shs) { preprocess_bwd_kernel<0><<<blocks, threads, 0, s>>>(p, io); return; }
-    switch (p.deg) {
-        case 0: preprocess_bwd_kernel<1><<<blocks, threads, 0, s>>>(p, io); break;
-        case 1: preprocess_bwd_kernel<4><<<blocks, threads, 0, s>>>(p, io); break;
-        case 2: preprocess_bwd_kernel<9><<<blocks, threads, 0, s>>>(p, io); break;
-        default: preprocess_bwd_kernel<16><<<blocks, threads, 0, s>>>(p, io); break;
-    }
+    // four lanes per Gaussian split the views of a multi-view launch; with one or two views (the reference renders one view per
+    // step, train.py:307) three of them would idle, so a Gaussian gets a single lane
+    if (p.V >= 3) launch_pbwd<4>(p, io, s); else launch_pbwd<1>(p, io, s);
 }

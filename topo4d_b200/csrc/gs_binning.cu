@@ -183,7 +183,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const GsParams
 
 // ---- K4 ----
 constexpr int SORT_THREADS = 128;
-constexpr int SORT_REG_KEYS = 2048;    // lists up to here are sorted in registers (<= 16 keys per thread); longer ones in place in HBM/L2
+constexpr int SORT_REG_KEYS = 2048;    // lists up to here are sorted in registers (<= 16 keys per thread) ...
+constexpr int SORT_LONG_THREADS = 1024;
+constexpr int SORT_LONG_KEYS = 16384;  // ... up to here by a 1024-thread CTA in 128 KB of shared memory (sort_gather_long_kernel: the reference's
+                                       // texture regime -- millions of pixel-sized splats -- has thousands of entries per tile); beyond, in place in HBM/L2
 
 // Generic bitonic network in the "flip / disperse" form on a key array in memory (used only for lists longer than
 // SORT_REG_KEYS): every compare-exchange moves the smaller key to the lower index, so virtual +inf padding above `n`
@@ -366,6 +369,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 8) sort_gather_kernel(const GsPa
         else if (n <= 128 * 4) sort_tile_regs<4>(gk, n, tid, s_keys);
         else if (n <= 128 * 8) sort_tile_regs<8>(gk, n, tid, s_keys);
         else if (n <= 128 * 16) sort_tile_regs<16>(gk, n, tid, s_keys);
+        else if (p.sort_long && n <= SORT_LONG_KEYS) continue;     // sort_gather_long_kernel owns this list (block-uniform)
         else {
             bitonic_sort_mem(gk, n, tid, SORT_THREADS);     // in place in L2-resident global memory
             sorted = gk;
@@ -399,6 +403,67 @@ __global__ void __launch_bounds__(SORT_THREADS, 8) sort_gather_kernel(const GsPa
     if (tid == 0) gs_queue_release(&p.status->q_sort, &p.status->done_sort, gridDim.x);
 }
 
+// Lists of 2049 .. 16384 keys: one 1024-thread CTA per tile, keys in (dynamic) shared memory, textbook bitonic network with
+// +inf padding up to the next power of two, then the same mask + gather epilogue as sort_gather_kernel.  Walks only the
+// front of active_tiles[] (the lists >= GS_LONG_TILE).  Launched when the host expects such lists (GsProblem.hints) or does
+// not know; sort_gather_kernel leaves them alone when this kernel runs and falls back to the in-place global network otherwise.
+__global__ void __launch_bounds__(SORT_LONG_THREADS, 1) sort_gather_long_kernel(const GsParams p)
+{
+    extern __shared__ __align__(16) unsigned long long s_long[];
+    __shared__ long long s_tile;
+    const int tid = threadIdx.x;
+    for (;;) {
+        if (tid == 0) {
+            const unsigned q = atomicAdd(&p.status->q_sort_long, 1u);
+            s_tile = q < p.status->num_long ? (long long)p.active_tiles[q] : -1;
+        }
+        __syncthreads();
+        const long long tg = s_tile;
+        __syncthreads();
+        if (tg < 0) break;
+        unsigned long long start = p.tile_start[tg], end = p.tile_start[tg + 1];
+        if (end > (unsigned long long)p.cap) end = (unsigned long long)p.cap;
+        if (end <= start + SORT_REG_KEYS || end > start + SORT_LONG_KEYS) continue;
+        const int n = (int)(end - start);
+        int n2 = SORT_REG_KEYS * 2;
+        while (n2 < n) n2 <<= 1;
+        const unsigned long long* __restrict__ gk = p.pairs + start;
+        for (int k = tid; k < n2; k += SORT_LONG_THREADS) s_long[k] = k < n ? gk[k] : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (n2 >> 1); t += SORT_LONG_THREADS) {
+                    const int i = 2 * t - (t & (j - 1)), l = i + j;
+                    const unsigned long long a = s_long[i], b = s_long[l];
+                    if ((a > b) == ((i & k) == 0)) { s_long[i] = b; s_long[l] = a; }
+                }
+                __syncthreads();
+            }
+        const int v = (int)(tg / p.tiles);
+        const float4* __restrict__ geom = p.geom + (size_t)v * p.N * 3;
+        float4* __restrict__ rec = p.sorted_rec + start * 3;
+        const int tl = (int)(tg - (long long)v * p.tiles);
+        const float tx0 = (float)((tl % p.tiles_x) * GS_TILE), ty0 = (float)((tl / p.tiles_x) * GS_TILE);
+        for (int k = tid; k < n; k += SORT_LONG_THREADS) {
+            const unsigned long long key = s_long[k];
+            const uint32_t id = (uint32_t)key & 0x00ffffffu;
+            p.sorted_ids[start + k] = id;
+            const unsigned mask = block_reach_mask(__ldg(geom + (size_t)id * 3), __ldg(geom + (size_t)id * 3 + 1), tx0, ty0);
+            s_long[k] = key | ((unsigned long long)mask << 24);
+        }
+        __syncthreads();
+        for (int t = tid; t < n * 3; t += SORT_LONG_THREADS) {
+            const int k = t / 3, part = t - k * 3;
+            const uint32_t low = (uint32_t)s_long[k];
+            float4 val = __ldg(geom + (size_t)(low & 0x00ffffffu) * 3 + part);
+            if (part == 2) val.w = __uint_as_float(low);           // id | reach mask << 24
+            rec[t] = val;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) gs_queue_release(&p.status->q_sort_long, &p.status->done_sort_long, gridDim.x);
+}
+
 }  // namespace
 
 void gs_launch_tile_scan(const GsParams& p, int num_sms, cudaStream_t s)
@@ -413,6 +478,14 @@ void gs_launch_tile_scan(const GsParams& p, int num_sms, cudaStream_t s)
 
 void gs_launch_sort_gather(const GsParams& p, int num_sms, cudaStream_t s)
 {
+    if (p.sort_long) {
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute((const void*)sort_gather_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_LONG_KEYS * 8);
+            attr_set = true;
+        }
+        sort_gather_long_kernel<<<num_sms, SORT_LONG_THREADS, SORT_LONG_KEYS * 8, s>>>(p);
+    }
     long long blocks = p.total_tiles;
     const long long maxb = (long long)num_sms * 8;
     if (blocks > maxb) blocks = maxb;

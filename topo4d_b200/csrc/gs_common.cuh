@@ -46,6 +46,7 @@ struct GsStatusDev {
     // (the first 48 bytes above are mirrored by the host layer; everything below is device-only)
     unsigned int scan_done;             // blocks of the fused tile scan that have published their total
     unsigned int done_sort, done_fwd, done_bwd;   // workers that have left a queue: the last one rewinds its cursor(s)
+    unsigned int q_sort_long, done_sort_long;     // queue of the long-list sort kernel (walks active_tiles[0 .. num_long))
 };
 #define GS_LONG_TILE 384                // longest-first work order: long lists are handed out before short ones
 #define GS_FILL_GROUP 16
@@ -114,6 +115,7 @@ struct GsParams {
     float4* grad2d;
     int scan_blocks;
     int blend_px;                       // pixels per thread of the blend kernels (1, 2, 4; see gs_blend.cu)
+    int sort_long;                      // 1: sort_gather_long_kernel takes the lists of 2049 .. 16384 keys (sort_gather_kernel skips them)
 };
 
 // launchers implemented in the kernel translation units

@@ -25,6 +25,7 @@ __device__ __constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f
                                         -0.5900435899266435f};
 
 struct Rect { int minx, miny, maxx, maxy; };
+constexpr int SH_ROW = 52;          // floats per staged SH row (48 + 4 padding: conflict-free 16-byte reads at lane stride)
 
 // tile rectangle of a splat: C truncation toward zero, then clamp to the grid (max exclusive)
 __device__ __forceinline__ Rect tile_rect(float pix_x, float pix_y, float radius, int gx, int gy)
@@ -39,17 +40,71 @@ __device__ __forceinline__ Rect tile_rect(float pix_x, float pix_y, float radius
     return r;
 }
 
-__global__ void __launch_bounds__(256, 3) preprocess_kernel(const GsParams p, int32_t* __restrict__ radii)
+// The kernel is latency-bound (a thread's work is a chain of dependent global loads and ~700 unfused fp32 operations; at 24 views
+// it issued at a fifth of the issue rate): the camera block of the (at most two) views a CTA touches is staged in shared memory,
+// and every per-Gaussian input -- the 12 16-byte SH loads included -- is requested at the top, before the projection and
+// covariance arithmetic that used to sit between a thread's loads, so ~20 loads per thread are in flight at once.  Registers
+// (up to 128 at 128-thread CTAs) are cheaper here than exposed L2 round trips.  Results are unchanged (same operations, same order).
+__global__ void __launch_bounds__(128, 4) preprocess_kernel(const GsParams p, int32_t* __restrict__ radii)
 {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)p.V * p.N) return;
+    __shared__ float s_cam[2][GS_CAM_FLOATS];
+    __shared__ __align__(16) float s_sh[4][32 * SH_ROW];
+    const long long gid0 = (long long)blockIdx.x * blockDim.x;
+    const int v_first = (int)(gid0 / p.N);
+    for (int k = threadIdx.x; k < 2 * GS_CAM_FLOATS; k += blockDim.x) {
+        const int vv = v_first + k / GS_CAM_FLOATS;
+        s_cam[k / GS_CAM_FLOATS][k % GS_CAM_FLOATS] = vv < p.V ? p.cams[(size_t)vv * GS_CAM_FLOATS + k % GS_CAM_FLOATS] : 0.f;
+    }
+    __syncthreads();
+    const long long gid_raw = gid0 + threadIdx.x;
+    const bool in_range = gid_raw < (long long)p.V * p.N;                        // out-of-range threads still help stage the SH rows
+    const long long gid = in_range ? gid_raw : 0;
     const int v = (int)(gid / p.N), i = (int)(gid % p.N);
-    const float* __restrict__ cam = p.cams + (size_t)v * GS_CAM_FLOATS;
+    const float* __restrict__ cam = s_cam[v - v_first];       // a 128-thread CTA spans at most two views (N >= 128) ...
+    if (v - v_first > 1) cam = p.cams + (size_t)v * GS_CAM_FLOATS;   // ... or reads global memory for the rest (tiny N)
     const float* V = cam + GS_CAM_VIEW;
     const float* P = cam + GS_CAM_PROJ;
-    radii[gid] = 0;
+    if (in_range) radii[gid] = 0;
 
+    // ---- all per-Gaussian inputs up front ----
     const float px = p.means3D[3 * i], py = p.means3D[3 * i + 1], pz = p.means3D[3 * i + 2];
+    const float opac = p.opac[i];
+    float in_s[3] = {0.f, 0.f, 0.f}, in_c3[6];
+    float4 in_q = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (p.cov3D) {
+        #pragma unroll
+        for (int k = 0; k < 6; k++) in_c3[k] = p.cov3D[6 * (size_t)i + k];
+    } else {
+        in_s[0] = p.scales[3 * i]; in_s[1] = p.scales[3 * i + 1]; in_s[2] = p.scales[3 * i + 2];
+        in_q = reinterpret_cast<const float4*>(p.rots)[i];
+    }
+    float in_col[3] = {0.f, 0.f, 0.f};
+    // SH rows: thread i owns 192 contiguous bytes, so per-thread 16-byte loads touch 32 different lines per instruction
+    // (ncu: the L1 data pipe at 55 % with 384 wavefronts per warp just for these).  The 32 rows of a warp are contiguous
+    // in memory (consecutive Gaussians), so the warp copies them with fully coalesced 16-byte loads into a padded
+    // shared-memory tile (row stride 52 floats: conflict-free 16-byte reads) and every thread reads its own row from there.
+    const bool sh_fast = p.shs != nullptr && p.M == 16 && ((reinterpret_cast<uintptr_t>(p.shs) & 15) == 0);
+    if (sh_fast) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int nf4 = ((p.deg + 1) * (p.deg + 1) * 3 + 3) / 4;                  // 16-byte chunks of a row that are needed
+        const long long g0 = gid0 + warp * 32;                                   // first (view, Gaussian) of this warp
+        const int i0 = (int)(g0 % p.N);
+        int r = lane / 12, q = lane - r * 12;                                    // chunk c = 32 k + lane = row r, 16-byte column q
+        const bool wraps = i0 + 32 > p.N;                                         // the warp straddles a view boundary (or N < 32)
+        #pragma unroll
+        for (int k = 0; k < 12; k++) {
+            int ir = i0 + r;
+            if (wraps && ir >= p.N) ir %= p.N;
+            if (q < nf4)
+                *reinterpret_cast<float4*>(&s_sh[warp][r * SH_ROW + 4 * q]) = __ldg(reinterpret_cast<const float4*>(p.shs + (size_t)ir * 48) + q);
+            q += 8; r += 2;                                                       // c += 32 = 2 rows + 8 columns
+            if (q >= 12) { q -= 12; r++; }
+        }
+        __syncwarp();
+    } else if (!p.shs) {
+        in_col[0] = p.colors[3 * i]; in_col[1] = p.colors[3 * i + 1]; in_col[2] = p.colors[3 * i + 2];
+    }
+    if (!in_range) return;
     const float tx = V[0] * px + V[4] * py + V[8] * pz + V[12];
     const float ty = V[1] * px + V[5] * py + V[9] * pz + V[13];
     const float tz = V[2] * px + V[6] * py + V[10] * pz + V[14];
@@ -64,10 +119,10 @@ __global__ void __launch_bounds__(256, 3) preprocess_kernel(const GsParams p, in
     float c3[6];
     if (p.cov3D) {
         #pragma unroll
-        for (int k = 0; k < 6; k++) c3[k] = p.cov3D[6 * (size_t)i + k];
+        for (int k = 0; k < 6; k++) c3[k] = in_c3[k];
     } else {
-        const float sx = p.mod * p.scales[3 * i], sy = p.mod * p.scales[3 * i + 1], sz = p.mod * p.scales[3 * i + 2];
-        const float4 q = reinterpret_cast<const float4*>(p.rots)[i];
+        const float sx = p.mod * in_s[0], sy = p.mod * in_s[1], sz = p.mod * in_s[2];
+        const float4 q = in_q;
         const float r = q.x, x = q.y, y = q.z, z = q.w;
         const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - r * z), R02 = 2.f * (x * z + r * y);
         const float R10 = 2.f * (x * y + r * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - r * x);
@@ -127,19 +182,18 @@ __global__ void __launch_bounds__(256, 3) preprocess_kernel(const GsParams p, in
     float rgb[3];
     unsigned clampbits = 0;
     if (p.shs) {
-        // coefficients of the active bands into registers: 16-byte loads when a Gaussian's row is 16-byte aligned
-        const float* __restrict__ shg = p.shs + (size_t)i * p.M * 3;
-        const int nf = (p.deg + 1) * (p.deg + 1) * 3;
         float sh[48];
-        if (((p.M * 3) & 3) == 0) {
-            const float4* __restrict__ sh4 = reinterpret_cast<const float4*>(shg);
+        const int nf = (p.deg + 1) * (p.deg + 1) * 3;
+        if (sh_fast) {
+            const float4* __restrict__ row = reinterpret_cast<const float4*>(&s_sh[threadIdx.x >> 5][(threadIdx.x & 31) * SH_ROW]);
             #pragma unroll
             for (int q = 0; q < 12; q++) {
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (q * 4 < nf) t = __ldg(sh4 + q);
+                if (q * 4 < nf) t = row[q];
                 sh[4 * q] = t.x; sh[4 * q + 1] = t.y; sh[4 * q + 2] = t.z; sh[4 * q + 3] = t.w;
             }
         } else {
+            const float* __restrict__ shg = p.shs + (size_t)i * p.M * 3;
             #pragma unroll
             for (int k = 0; k < 48; k++) sh[k] = k < nf ? __ldg(shg + k) : 0.f;
         }
@@ -172,7 +226,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_kernel(const GsParams p, in
             rgb[ch] = res;
         }
     } else {
-        rgb[0] = p.colors[3 * i]; rgb[1] = p.colors[3 * i + 1]; rgb[2] = p.colors[3 * i + 2];
+        rgb[0] = in_col[0]; rgb[1] = in_col[1]; rgb[2] = in_col[2];
     }
 
     radii[gid] = (int)radius;
@@ -182,7 +236,6 @@ __global__ void __launch_bounds__(256, 3) preprocess_kernel(const GsParams p, in
     // thr: the blend kernels skip a pixel without evaluating exp() when power < thr.  alpha >= 1/255 needs
     // power >= -ln(255*opacity); the 1e-3 margin (0.1 % in alpha) dwarfs any fp32 rounding of power or exp,
     // so the prefilter can only pass extra pixels (which then fail the exact alpha test), never drop one.
-    const float opac = p.opac[i];
     const float thr = opac > 0.0f ? fmaxf(-logf(255.0f * opac) - 1.0e-3f, -1.0e20f) : __int_as_float(0x7f800000);   // >= -1e20: see PARKED_Y in gs_blend.cu
     g[1] = make_float4(cC, opac, tz, thr);
     g[2] = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(i));
@@ -230,7 +283,7 @@ void gs_launch_preprocess(const GsParams& p, int32_t* radii, cudaStream_t s)
 {
     const long long n = (long long)p.V * p.N;
     if (n == 0) return;
-    preprocess_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, radii);
+    preprocess_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p, radii);
 }
 
 void gs_launch_scatter(const GsParams& p, const int32_t* radii, cudaStream_t s)

@@ -28,6 +28,7 @@ _COUNT_MEMO: dict[tuple, int] = {}  # last measured (tile, Gaussian) instance co
 _TOUCHED_KEYS: set = set()         # problem shapes rendered since the set was last cleared (graph.capture sizes headroom)
 # remembered number of non-empty tiles per problem shape: picks the blend kernels' pixels-per-thread variant
 _ACTIVE_MEMO: dict[tuple, int] = {}
+_MAXTILE_MEMO: dict[tuple, int] = {}  # longest per-tile list per problem shape: tells the library whether the long-list sort kernel is needed
 _WS_BYTES: dict[tuple, int] = {}
 ctypes_sizeof_status_dev = 48      # sizeof(GsStatusDev), csrc/gs_common.cuh (layout mirrored in RasterState.status)
 _PINNED_RING = None                # one pinned allocation, 256 status slots handed out round-robin
@@ -119,6 +120,7 @@ class RasterState:
             if self.key:
                 _ACTIVE_MEMO[self.key] = int(st.num_active_tiles)
                 _COUNT_MEMO[self.key] = int(st.num_instances)
+                _MAXTILE_MEMO[self.key] = int(st.max_tile_instances)
         if self._status is None:
             st = GsStatus()
             with torch.cuda.device(self.device):
@@ -130,6 +132,7 @@ class RasterState:
             if self.key:
                 _ACTIVE_MEMO[self.key] = int(st.num_active_tiles)
                 _COUNT_MEMO[self.key] = int(st.num_instances)
+                _MAXTILE_MEMO[self.key] = int(st.max_tile_instances)
         return self._status
 
     def view(self) -> dict:
@@ -208,6 +211,9 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
     _TOUCHED_KEYS.add(key)
     cap = int(cap_instances) if cap_instances is not None else _CAP_MEMO.get(key)
     px = int(blend_px) if blend_px else pick_blend_px(_ACTIVE_MEMO.get(key))
+    mt = _MAXTILE_MEMO.get(key)
+    # lists a little under the 2048-key limit may grow past it while the splats move: keep the long-list kernel from 1536 up
+    hints = _lib.GS_HINT_UNKNOWN if mt is None else (_lib.GS_HINT_SHORT_LISTS if mt <= 1536 else _lib.GS_HINT_LONG_LISTS)
 
     def make_problem(cap_):
         wk = (N, V, H, W, cap_)
@@ -215,7 +221,7 @@ def forward(means3D, opacities, cameras, image_height, image_width, *, shs=None,
         if nbytes is None:
             nbytes = _WS_BYTES[wk] = L.gs_workspace_bytes(N, V, H, W, cap_)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        pr = GsProblem(N, V, H, W, int(sh_degree), M, float(scale_modifier), int(bool(debug)), px, 0, cap_,
+        pr = GsProblem(N, V, H, W, int(sh_degree), M, float(scale_modifier), int(bool(debug)), px, hints, cap_,
                        _ptr(means3D), _ptr(shs), _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
                        _ptr(cov3D_precomp), _ptr(cameras), _ptr(ws), nbytes)
         return pr, ws
