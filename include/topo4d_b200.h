@@ -197,6 +197,20 @@ size_t f3d_workspace_bytes(int32_t ntri, int32_t h, int32_t w);
 int f3d_render_colors(float* image, const float* vertices, const int32_t* triangles, const float* colors,
                       float* depth_buffer, int32_t nver, int32_t ntri, int32_t h, int32_t w, int32_t c,
                       void* workspace, size_t workspace_bytes, gs_stream_t stream);
+/* Scratch budget per key plane (calling thread; <= 0 restores the default of 1 GiB = the whole image up to 16384^2): larger
+ * images are resolved in bands of rows.  Call before f3d_workspace_bytes.  Results never depend on it. */
+void f3d_set_band_bytes(int64_t bytes);
+/* The bake as face3d/mesh/render.py:52-86 performs it (fresh zero image, private depth buffer filled with `depth_init` =
+ * -999999 and discarded): writes EVERY pixel of `image` [h,w,c] fp32 or -- fused epilogue of helpers.py:959 -- of
+ * `image_u8` [h,w,c] = (uint8)(value*255); exactly one of the two is non-NULL; no depth plane is read or written. */
+int f3d_bake_colors(float* image, uint8_t* image_u8, const float* vertices, const int32_t* triangles, const float* colors,
+                    float depth_init, int32_t nver, int32_t ntri, int32_t h, int32_t w, int32_t c,
+                    void* workspace, size_t workspace_bytes, gs_stream_t stream);
+/* HOST-pointer path, the calling convention of `render_colors_core` (face3d/mesh/cython/mesh_core_cython.pyx:64-77):
+ * C-contiguous host arrays, image [h,w,c] and depth_buffer [h,w] updated in place, complete on return.  Copies and
+ * device scratch are handled inside (the only entry point that allocates device memory: stream-ordered, freed on return). */
+int f3d_render_colors_host(float* image, const float* vertices, const int32_t* triangles, const float* colors,
+                           float* depth_buffer, int32_t nver, int32_t ntri, int32_t h, int32_t w, int32_t c);
 /* Optional fused epilogue of helpers.py:959: out_u8[h,w,c] = (uint8)(image*255) (C truncation). */
 int f3d_image_to_u8(const float* image, uint8_t* out_u8, int64_t count, gs_stream_t stream);
 

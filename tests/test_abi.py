@@ -46,7 +46,10 @@ def test_workspace_bytes_arithmetic():
     per_view = (a - c) / 23
     assert per_view >= 1080 * 1920 * 8 + 60000 * 97                  # final_T + n_contrib + geom + grad2d + clamp
     assert L.gs_workspace_bytes(-1, 1, 8, 8, 0) == 0 and L.gs_workspace_bytes(1, 0, 8, 8, 0) == 0
-    assert L.f3d_workspace_bytes(10, 8192, 8192) == 8192 * 8192 * 8
+    # face3d: header + two u32 key planes for one band of rows (<= 1 GiB per plane: the whole image at 8192^2)
+    assert L.f3d_workspace_bytes(10, 8192, 8192) == 256 + 2 * 8192 * 8192 * 4
+    assert L.f3d_workspace_bytes(10, 32768, 32768) == 256 + 2 * 8192 * 32768 * 4
+    assert L.f3d_workspace_bytes(10, 64, 48) == 256 + 2 * 64 * 48 * 4 and L.f3d_workspace_bytes(10, 0, 8) == 0
 
 
 def test_argument_validation_without_gpu():
@@ -57,6 +60,8 @@ def test_argument_validation_without_gpu():
     assert L.gs_forward(C.byref(pr), C.byref(out), None) == _lib.GS_E_BAD_ARGS           # no workspace / cameras
     assert L.gs_backward(C.byref(pr), None, None) == _lib.GS_E_BAD_ARGS
     assert L.f3d_render_colors(None, None, None, None, None, 0, 0, 8, 8, 3, None, 0, None) == -1
+    assert L.f3d_bake_colors(None, None, None, None, None, 0.0, 0, 0, 8, 8, 3, None, 0, None) == -1
+    assert L.f3d_render_colors_host(None, None, None, None, None, 0, 0, 8, 8, 3) == -1
     assert b"capacity" in L.gs_last_error(_lib.GS_E_OVERFLOW)
     with pytest.raises(_lib.GsError):
         _lib.check(_lib.GS_E_WORKSPACE_SMALL, "x")

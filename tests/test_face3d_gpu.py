@@ -86,3 +86,33 @@ def test_full_size_properties_8k():
     ref_small, _ = _cpu(vs, ts, cs, 256, 256, 3)
     np.testing.assert_array_equal(f3d_render.render_colors_u8(vs, ts, cs, 256, 256, 3), (ref_small * 255).astype(np.uint8))
     assert float((img.sum(-1) != 0).float().mean()) > 0.95
+
+
+@pytest.mark.parametrize("zmode", ["flat", "random"])
+def test_fused_bake_path_float_and_u8(zmode):
+    """render_colors without BG takes the fused bake (f3d_bake_colors: fresh image, private constant depth, optional uint8):
+    bit-identical to the reference followed by (image * 255).astype(uint8), for all-zero z (one key stage) and general z (two)."""
+    v, t, c = synth.uv_grid_mesh(grid=40, res=300, seed=7)
+    if zmode == "random":
+        v[:, 2] = np.random.default_rng(3).normal(size=v.shape[0])
+    ref, _ = _cpu(v, t, c, 300, 300, 3)
+    np.testing.assert_array_equal(f3d_render.render_colors(v, t, c, 300, 300, 3), ref)
+    np.testing.assert_array_equal(f3d_render.render_colors_u8(v, t, c, 300, 300, 3), (ref * 255).astype(np.uint8))
+    # an empty mesh still yields the zero image (render.py:66)
+    assert not f3d_render.render_colors(v, t[:0], c, 64, 48, 3).any()
+
+
+def test_row_bands_do_not_change_results():
+    """Images beyond the scratch budget are resolved in bands of rows; force 16-row bands on a small image."""
+    from topo4d_b200 import _lib
+    v, t, c = synth.uv_grid_mesh(grid=23, res=200, seed=11)
+    v[:, 2] = np.random.default_rng(5).normal(size=v.shape[0])
+    ref, _ = _cpu(v, t, c, 200, 200, 3)
+    try:
+        _lib.lib().f3d_set_band_bytes(16 * 200 * 4)
+        np.testing.assert_array_equal(f3d_render.render_colors(v, t, c, 200, 200, 3), ref)
+        bg = np.full((200, 200, 3), 0.5, np.float32)
+        ref_bg, _ = _cpu(v, t, c, 200, 200, 3, BG=bg.copy())
+        np.testing.assert_array_equal(f3d_render.render_colors(v, t, c, 200, 200, 3, BG=bg), ref_bg)
+    finally:
+        _lib.lib().f3d_set_band_bytes(0)

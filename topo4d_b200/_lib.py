@@ -79,6 +79,10 @@ SYMBOLS = {
     "f3d_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "f3d_render_colors": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     _vp, C.c_size_t, _vp]),
+    "f3d_set_band_bytes": (None, [C.c_int64]),
+    "f3d_bake_colors": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  _vp, C.c_size_t, _vp]),
+    "f3d_render_colors_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "f3d_image_to_u8": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "t4d_image_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "t4d_image_loss": (C.c_int, [C.POINTER(T4dImageLoss), _vp]),

@@ -9,12 +9,15 @@
 // p_depth > depth_buffer (strict).  That is order-free equivalent to: per pixel, the winner is
 // the triangle maximising (p_depth, -index) among those accepting the pixel, drawn iff its
 // p_depth > the initial depth.  Two passes:
-//   pass 1  (triangle-parallel) atomicMax of a 64-bit key (orderable(p_depth)<<32 | ~index) per
-//           accepted bbox pixel; a warp takes 32 triangles, small boxes are walked by their own
-//           lane, large boxes cooperatively by the whole warp;
-//   pass 2  (pixel-parallel, coalesced) decode the winner, recompute its weights (same bits),
-//           depth-test against the caller's depth buffer, write c channels + depth in place.
-// Roofline: HBM -- h*w*(8 key + 8 key re-read + 4c image + 8 depth) bytes; no data reuse worth smem.
+//   stage 0/1 (triangle-parallel) 32-bit atomicMax of orderable(p_depth), then of ~index among the
+//           triangles at that depth, per accepted bbox pixel; a warp takes 32 triangles, small boxes are
+//           walked by their own lane, large boxes cooperatively by the whole warp; stage 0 is skipped
+//           when every vertex z is 0 (the texture bake);
+//   shade   (pixel-parallel, coalesced) decode the winner, recompute its weights (same bits),
+//           depth-test, write c channels (+ depth) -- optionally filling the background and / or
+//           converting to uint8 in the same pass.
+// The image is resolved in bands of rows whose key planes stay in L2.  Roofline: HBM, h*w*4c bytes written
+// (+ the caller's depth plane read and written when the in-place depth contract is used).
 #include "gs_common.cuh"
 
 namespace {
@@ -49,12 +52,12 @@ __device__ __forceinline__ bool accepts(int x, int y, int h, int w, bool inside)
     return fx < 2.0f || fx > (float)(w - 3) || fy < 2.0f || fy > (float)(h - 3) || inside;
 }
 
-__device__ __forceinline__ unsigned long long make_key(float depth, int index)
+// order-preserving map fp32 -> u32 (NaN never reaches it); +0 and -0 compare equal in the reference's strict '>' test
+__device__ __forceinline__ unsigned orderable(float depth)
 {
     unsigned b = __float_as_uint(depth);
-    if (depth == 0.0f) b = 0u;                               // -0 == +0 for the strict '>' test
-    const unsigned ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-    return ((unsigned long long)ord << 32) | (unsigned long long)(0xffffffffu - (unsigned)index);
+    if (depth == 0.0f) b = 0u;
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
 __device__ __forceinline__ int clamp_to_int(float f)
@@ -64,7 +67,7 @@ __device__ __forceinline__ int clamp_to_int(float f)
 }
 
 __device__ __forceinline__ bool load_tri(const float* __restrict__ vertices, const int* __restrict__ triangles,
-                                         int i, int nver, int h, int w, Tri& t)
+                                         int i, int nver, int h, int w, int y_lo, int y_hi, Tri& t)
 {
     const int i0 = triangles[3 * i], i1 = triangles[3 * i + 1], i2 = triangles[3 * i + 2];
     if ((unsigned)i0 >= (unsigned)nver || (unsigned)i1 >= (unsigned)nver || (unsigned)i2 >= (unsigned)nver) return false;
@@ -73,28 +76,38 @@ __device__ __forceinline__ bool load_tri(const float* __restrict__ vertices, con
     t.x2 = vertices[3 * i2]; t.y2 = vertices[3 * i2 + 1]; t.z2 = vertices[3 * i2 + 2];
     t.xmin = max(clamp_to_int(ceilf(fminf(t.x0, fminf(t.x1, t.x2)))), 0);
     t.xmax = min(clamp_to_int(floorf(fmaxf(t.x0, fmaxf(t.x1, t.x2)))), w - 1);
-    t.ymin = max(clamp_to_int(ceilf(fminf(t.y0, fminf(t.y1, t.y2)))), 0);
-    t.ymax = min(clamp_to_int(floorf(fmaxf(t.y0, fmaxf(t.y1, t.y2)))), h - 1);
+    t.ymin = max(max(clamp_to_int(ceilf(fminf(t.y0, fminf(t.y1, t.y2)))), 0), y_lo);          // clipped to the band of rows
+    t.ymax = min(min(clamp_to_int(floorf(fmaxf(t.y0, fmaxf(t.y1, t.y2)))), h - 1), y_hi);     // this launch resolves
     return !(t.xmax < t.xmin || t.ymax < t.ymin);
 }
 
-__device__ __forceinline__ void test_pixel(const Tri& t, int idx, int x, int y, int h, int w,
-                                           unsigned long long* __restrict__ keys)
+// Per-pixel winner = the accepting triangle maximising (p_depth, -index).  With 32-bit atomics only:
+//   STAGE 0  dmax[pix] = max orderable(p_depth)                     (skipped when every vertex z is 0: all depths are +-0)
+//   STAGE 1  imax[pix] = max (~index) over the accepting triangles whose depth equals dmax[pix]
+// (the r01 kernel used one 64-bit atomicMax on depth << 32 | ~index: twice the key traffic, half the atomic rate)
+template <int STAGE>
+__device__ __forceinline__ void test_pixel(const Tri& t, int idx, int x, int y, int h, int w, int y_lo, bool flat,
+                                           unsigned* __restrict__ dmax, unsigned* __restrict__ imax)
 {
     float w0, w1, w2; bool inside;
     bary((float)x, (float)y, t, w0, w1, w2, inside);
     if (!accepts(x, y, h, w, inside)) return;
     const float d = w0 * t.z0 + w1 * t.z1 + w2 * t.z2;
     if (d != d) return;                                      // NaN never passes '>' in the reference
-    atomicMax(keys + (size_t)y * w + x, make_key(d, idx));
+    const size_t pix = (size_t)(y - y_lo) * w + x;
+    if (STAGE == 0) atomicMax(dmax + pix, orderable(d));
+    else if (flat || dmax[pix] == orderable(d)) atomicMax(imax + pix, 0xffffffffu - (unsigned)idx);
 }
 
 constexpr int SMALL_BOX = 48;   // bbox pixels a single lane walks by itself
 
+template <int STAGE>
 __global__ void __launch_bounds__(256)
-f3d_pass1_kernel(const float* __restrict__ vertices, const int* __restrict__ triangles, int nver, int ntri, int h, int w,
-                 unsigned long long* __restrict__ keys)
+f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ triangles, int nver, int ntri, int h, int w,
+               int y_lo, int y_hi, const int* __restrict__ nonflat, unsigned* __restrict__ dmax, unsigned* __restrict__ imax)
 {
+    const bool flat = *nonflat == 0;
+    if (STAGE == 0 && flat) return;
     const int lane = threadIdx.x & 31;
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -102,12 +115,12 @@ f3d_pass1_kernel(const float* __restrict__ vertices, const int* __restrict__ tri
         const int i = (int)(base + lane);
         Tri t;
         bool ok = false;
-        if (i < ntri) ok = load_tri(vertices, triangles, i, nver, h, w, t);
+        if (i < ntri) ok = load_tri(vertices, triangles, i, nver, h, w, y_lo, y_hi, t);
         int bw = 0, area = 0;
         if (ok) { bw = t.xmax - t.xmin + 1; const long long a = (long long)bw * (t.ymax - t.ymin + 1); area = a > 0x7fffffffLL ? 0x7fffffff : (int)a; }
         if (ok && area <= SMALL_BOX) {
             for (int y = t.ymin; y <= t.ymax; y++)
-                for (int x = t.xmin; x <= t.xmax; x++) test_pixel(t, i, x, y, h, w, keys);
+                for (int x = t.xmin; x <= t.xmax; x++) test_pixel<STAGE>(t, i, x, y, h, w, y_lo, flat, dmax, imax);
         }
         unsigned big = __ballot_sync(0xffffffffu, ok && area > SMALL_BOX);
         while (big) {
@@ -125,7 +138,7 @@ f3d_pass1_kernel(const float* __restrict__ vertices, const int* __restrict__ tri
             int xx = lane, yy = 0;
             while (xx >= sbw) { xx -= sbw; yy++; }
             for (int k = lane; k < sarea; k += 32) {
-                test_pixel(s, sidx, s.xmin + xx, s.ymin + yy, h, w, keys);
+                test_pixel<STAGE>(s, sidx, s.xmin + xx, s.ymin + yy, h, w, y_lo, flat, dmax, imax);
                 xx += 32;
                 while (xx >= sbw) { xx -= sbw; yy++; }
             }
@@ -133,43 +146,79 @@ f3d_pass1_kernel(const float* __restrict__ vertices, const int* __restrict__ tri
     }
 }
 
-__global__ void __launch_bounds__(256)
-f3d_pass2_kernel(float* __restrict__ image, const float* __restrict__ vertices, const int* __restrict__ triangles,
-                 const float* __restrict__ colors, float* __restrict__ depth, int nver, int ntri, int h, int w, int c,
-                 const unsigned long long* __restrict__ keys)
+__global__ void __launch_bounds__(256) f3d_clear_if_nonflat_kernel(unsigned* __restrict__ plane, size_t n, const int* __restrict__ nonflat)
 {
-    // one thread per pixel, rows from blockIdx.y (grid-strided): no integer division, coalesced key/depth/image rows
+    if (*nonflat == 0) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) plane[i] = 0u;
+}
+
+__global__ void __launch_bounds__(256) f3d_flat_kernel(const float* __restrict__ vertices, int nver, int* __restrict__ nonflat)
+{
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nver; i += (long long)gridDim.x * blockDim.x)
+        bad = bad || !(vertices[3 * i + 2] == 0.0f);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(nonflat, 1);
+}
+
+// Pixel-parallel resolve of rows [y_lo, y_hi]: decode the winner, recompute its weights (same bits), depth-test against the
+// caller's depth buffer -- or against the constant `depth_init` when the caller has none (face3d/mesh/render.py:68 creates its
+// own, filled with -999999, and throws it away: 268 MB of reads and 268 MB of writes at 8192^2 for nothing) -- and write.
+// FILL: the image is uninitialised; uncovered pixels receive zeros here (render.py:66 np.zeros) instead of a separate 805 MB
+// clear.  U8: write (uint8)(value * 255) (helpers.py:959) instead of fp32: a quarter of the bytes.
+template <bool FILL, bool U8>
+__global__ void __launch_bounds__(256)
+f3d_shade_kernel(float* __restrict__ image, uint8_t* __restrict__ image_u8, const float* __restrict__ vertices,
+                 const int* __restrict__ triangles, const float* __restrict__ colors, float* __restrict__ depth, float depth_init,
+                 int nver, int ntri, int h, int w, int c, int y_lo, int y_hi, const unsigned* __restrict__ imax)
+{
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
-    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    for (int y = y_lo + blockIdx.y; y <= y_hi; y += gridDim.y) {
         const size_t pix = (size_t)y * w + x;
-        const unsigned long long key = keys[pix];
-        if (key == 0ull) continue;
-        const int idx = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
-        if (idx < 0 || idx >= ntri) continue;
-        const int i0 = triangles[3 * idx], i1 = triangles[3 * idx + 1], i2 = triangles[3 * idx + 2];
-        Tri t;
-        t.x0 = vertices[3 * i0]; t.y0 = vertices[3 * i0 + 1]; t.z0 = vertices[3 * i0 + 2];
-        t.x1 = vertices[3 * i1]; t.y1 = vertices[3 * i1 + 1]; t.z1 = vertices[3 * i1 + 2];
-        t.x2 = vertices[3 * i2]; t.y2 = vertices[3 * i2 + 1]; t.z2 = vertices[3 * i2 + 2];
-        float w0, w1, w2; bool inside;
-        bary((float)x, (float)y, t, w0, w1, w2, inside);
-        const float d = w0 * t.z0 + w1 * t.z1 + w2 * t.z2;
-        if (!(d > depth[pix])) continue;
-        if (c == 3) {
-            const float* __restrict__ a0 = colors + 3 * (size_t)i0; const float* __restrict__ a1 = colors + 3 * (size_t)i1;
-            const float* __restrict__ a2 = colors + 3 * (size_t)i2;
-            float* __restrict__ o = image + pix * 3;
-            o[0] = w0 * a0[0] + w1 * a1[0] + w2 * a2[0];
-            o[1] = w0 * a0[1] + w1 * a1[1] + w2 * a2[1];
-            o[2] = w0 * a0[2] + w1 * a1[2] + w2 * a2[2];
-        } else {
-            for (int k = 0; k < c; k++) {
-                const float c0 = colors[(size_t)c * i0 + k], c1 = colors[(size_t)c * i1 + k], c2 = colors[(size_t)c * i2 + k];
-                image[pix * c + k] = w0 * c0 + w1 * c1 + w2 * c2;
+        const unsigned key = imax[(size_t)(y - y_lo) * w + x];
+        bool drawn = false;
+        float col[3] = {0.f, 0.f, 0.f};
+        int i0 = 0, i1 = 0, i2 = 0;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+        if (key != 0u) {
+            const int idx = (int)(0xffffffffu - key);
+            if (idx >= 0 && idx < ntri) {
+                i0 = triangles[3 * idx]; i1 = triangles[3 * idx + 1]; i2 = triangles[3 * idx + 2];
+                Tri t;
+                t.x0 = vertices[3 * i0]; t.y0 = vertices[3 * i0 + 1]; t.z0 = vertices[3 * i0 + 2];
+                t.x1 = vertices[3 * i1]; t.y1 = vertices[3 * i1 + 1]; t.z1 = vertices[3 * i1 + 2];
+                t.x2 = vertices[3 * i2]; t.y2 = vertices[3 * i2 + 1]; t.z2 = vertices[3 * i2 + 2];
+                bool inside;
+                bary((float)x, (float)y, t, w0, w1, w2, inside);
+                const float d = w0 * t.z0 + w1 * t.z1 + w2 * t.z2;
+                drawn = d > (depth ? depth[pix] : depth_init);
+                if (drawn && depth) depth[pix] = d;
             }
         }
-        depth[pix] = d;
+        if (c == 3) {
+            if (drawn) {
+                const float* __restrict__ a0 = colors + 3 * (size_t)i0; const float* __restrict__ a1 = colors + 3 * (size_t)i1;
+                const float* __restrict__ a2 = colors + 3 * (size_t)i2;
+                col[0] = w0 * a0[0] + w1 * a1[0] + w2 * a2[0];
+                col[1] = w0 * a0[1] + w1 * a1[1] + w2 * a2[1];
+                col[2] = w0 * a0[2] + w1 * a1[2] + w2 * a2[2];
+            }
+            if (drawn || FILL) {
+                if (U8) {
+                    uint8_t* __restrict__ o = image_u8 + pix * 3;
+                    o[0] = (unsigned char)(int)(col[0] * 255.0f); o[1] = (unsigned char)(int)(col[1] * 255.0f); o[2] = (unsigned char)(int)(col[2] * 255.0f);
+                } else {
+                    float* __restrict__ o = image + pix * 3;
+                    o[0] = col[0]; o[1] = col[1]; o[2] = col[2];
+                }
+            }
+        } else if (drawn || FILL) {
+            for (int k = 0; k < c; k++) {
+                float v = 0.f;
+                if (drawn) v = w0 * colors[(size_t)c * i0 + k] + w1 * colors[(size_t)c * i1 + k] + w2 * colors[(size_t)c * i2 + k];
+                if (U8) image_u8[pix * c + k] = (unsigned char)(int)(v * 255.0f); else image[pix * c + k] = v;
+            }
+        }
     }
 }
 
@@ -191,35 +240,125 @@ __global__ void __launch_bounds__(256) f3d_to_u8_kernel(const float* __restrict_
 
 }  // namespace
 
-extern "C" size_t f3d_workspace_bytes(int32_t ntri, int32_t h, int32_t w)
+// Workspace: a 256-byte header (the "some vertex z != 0" flag) and two u32 key planes for one BAND of rows; with all z = 0
+// (the texture bake: helpers.py:945-950) only one plane is used.  Bands exist so that images beyond the budget still resolve
+// with bounded scratch; at 8192^2 the whole image is ONE band.  (Measured, r02: resolving 8192^2 in L2-sized bands of 768 rows
+// was 3x SLOWER -- 3.5 ms vs 1.1 ms -- because every band re-walks the triangle list and, triangles being stored row by row,
+// only the ~9 % of the warps whose 32 triangles touch the band have work.)
+#ifndef F3D_BAND_BYTES
+#define F3D_BAND_BYTES (1ll << 30)
+#endif
+static thread_local long long g_band_bytes = F3D_BAND_BYTES;
+extern "C" void f3d_set_band_bytes(int64_t bytes) { g_band_bytes = bytes > 0 ? bytes : F3D_BAND_BYTES; }
+
+static int f3d_band_rows(int ntri, int h, int w)
 {
     (void)ntri;
+    const long long budget = g_band_bytes;                        // bytes per key plane and band
+    long long rows = budget / ((long long)w * 4);
+    if (rows < 16) rows = 16;
+    if (rows > h) rows = h;
+    return (int)rows;
+}
+
+extern "C" size_t f3d_workspace_bytes(int32_t ntri, int32_t h, int32_t w)
+{
     if (h < 1 || w < 1) return 0;
-    return (size_t)h * (size_t)w * sizeof(unsigned long long);
+    return 256 + 2 * (size_t)f3d_band_rows(ntri, h, w) * (size_t)w * sizeof(unsigned);
+}
+
+static int f3d_run(float* image, uint8_t* image_u8, bool fill, const float* vertices, const int32_t* triangles, const float* colors,
+                   float* depth_buffer, float depth_init, int32_t nver, int32_t ntri, int32_t h, int32_t w, int32_t c,
+                   void* workspace, size_t workspace_bytes, cudaStream_t s)
+{
+    if ((!image && !image_u8) || h < 1 || w < 1 || c < 1 || nver < 0 || ntri < 0) return F3D_E_BAD_ARGS;
+    if (ntri > 0 && (!vertices || !triangles || !colors)) return F3D_E_BAD_ARGS;
+    if (!workspace || workspace_bytes < f3d_workspace_bytes(ntri, h, w)) return F3D_E_WORKSPACE;
+    if (ntri == 0 && !fill) return F3D_OK;
+    const int band = f3d_band_rows(ntri, h, w);
+    int* nonflat = (int*)workspace;
+    unsigned* imax = (unsigned*)((char*)workspace + 256);
+    unsigned* dmax = imax + (size_t)band * w;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaMemsetAsync(nonflat, 0, 256, s) != cudaSuccess) return F3D_E_CUDA;
+    if (nver > 0) f3d_flat_kernel<<<sms * 2, 256, 0, s>>>(vertices, nver, nonflat);
+    const long long warps_needed = ((long long)ntri + 31) / 32;
+    long long blocks1 = (warps_needed + 7) / 8;
+    if (blocks1 > (long long)sms * 64) blocks1 = (long long)sms * 64;
+    if (blocks1 < 1) blocks1 = 1;
+    for (int y_lo = 0; y_lo < h; y_lo += band) {
+        const int y_hi = (y_lo + band < h ? y_lo + band : h) - 1, rows = y_hi - y_lo + 1;
+        if (cudaMemsetAsync(imax, 0, (size_t)band * w * sizeof(unsigned), s) != cudaSuccess) return F3D_E_CUDA;
+        f3d_clear_if_nonflat_kernel<<<sms * 4, 256, 0, s>>>(dmax, (size_t)band * w, nonflat);      // the depth plane only when it will be used
+        if (ntri > 0) {
+            f3d_tri_kernel<0><<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, y_lo, y_hi, nonflat, dmax, imax);
+            f3d_tri_kernel<1><<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, y_lo, y_hi, nonflat, dmax, imax);
+        }
+        const dim3 grid2((unsigned)((w + 255) / 256), (unsigned)(rows < 65535 ? rows : 65535));
+        if (fill && image_u8)
+            f3d_shade_kernel<true, true><<<grid2, 256, 0, s>>>(image, image_u8, vertices, triangles, colors, depth_buffer, depth_init, nver, ntri, h, w, c, y_lo, y_hi, imax);
+        else if (fill)
+            f3d_shade_kernel<true, false><<<grid2, 256, 0, s>>>(image, image_u8, vertices, triangles, colors, depth_buffer, depth_init, nver, ntri, h, w, c, y_lo, y_hi, imax);
+        else if (image_u8)
+            f3d_shade_kernel<false, true><<<grid2, 256, 0, s>>>(image, image_u8, vertices, triangles, colors, depth_buffer, depth_init, nver, ntri, h, w, c, y_lo, y_hi, imax);
+        else
+            f3d_shade_kernel<false, false><<<grid2, 256, 0, s>>>(image, image_u8, vertices, triangles, colors, depth_buffer, depth_init, nver, ntri, h, w, c, y_lo, y_hi, imax);
+    }
+    return cudaGetLastError() == cudaSuccess ? F3D_OK : F3D_E_CUDA;
 }
 
 extern "C" int f3d_render_colors(float* image, const float* vertices, const int32_t* triangles, const float* colors,
                                  float* depth_buffer, int32_t nver, int32_t ntri, int32_t h, int32_t w, int32_t c,
                                  void* workspace, size_t workspace_bytes, gs_stream_t stream)
 {
+    if (!image || !depth_buffer) return F3D_E_BAD_ARGS;
+    return f3d_run(image, nullptr, false, vertices, triangles, colors, depth_buffer, 0.f, nver, ntri, h, w, c, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int f3d_bake_colors(float* image, uint8_t* image_u8, const float* vertices, const int32_t* triangles, const float* colors,
+                               float depth_init, int32_t nver, int32_t ntri, int32_t h, int32_t w, int32_t c,
+                               void* workspace, size_t workspace_bytes, gs_stream_t stream)
+{
+    if ((image != nullptr) == (image_u8 != nullptr)) return F3D_E_BAD_ARGS;       // exactly one output format
+    return f3d_run(image, image_u8, true, vertices, triangles, colors, nullptr, depth_init, nver, ntri, h, w, c, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
+}
+
+// Host-pointer entry with the calling convention of the reference's Cython shim (mesh_core_cython.pyx:64-77): every pointer
+// is HOST memory, `image` [h,w,c] and `depth_buffer` [h,w] are read, updated in place and complete on return.  The one entry
+// point of the library that owns device memory (stream-ordered allocations, released before returning).
+extern "C" int f3d_render_colors_host(float* image, const float* vertices, const int32_t* triangles, const float* colors,
+                                      float* depth_buffer, int32_t nver, int32_t ntri, int32_t h, int32_t w, int32_t c)
+{
     if (!image || !depth_buffer || h < 1 || w < 1 || c < 1 || nver < 0 || ntri < 0) return F3D_E_BAD_ARGS;
     if (ntri > 0 && (!vertices || !triangles || !colors)) return F3D_E_BAD_ARGS;
-    if (!workspace || workspace_bytes < f3d_workspace_bytes(ntri, h, w)) return F3D_E_WORKSPACE;
     if (ntri == 0) return F3D_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long* keys = (unsigned long long*)workspace;
-    cudaError_t e = cudaMemsetAsync(keys, 0, (size_t)h * w * sizeof(unsigned long long), s);
-    if (e != cudaSuccess) return F3D_E_CUDA;
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long warps_needed = ((long long)ntri + 31) / 32;
-    long long blocks1 = (warps_needed + 7) / 8;
-    if (blocks1 > (long long)sms * 64) blocks1 = (long long)sms * 64;
-    f3d_pass1_kernel<<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, keys);
-    const dim3 grid2((unsigned)((w + 255) / 256), (unsigned)(h < 65535 ? h : 65535));
-    f3d_pass2_kernel<<<grid2, 256, 0, s>>>(image, vertices, triangles, colors, depth_buffer, nver, ntri, h, w, c, keys);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? F3D_OK : F3D_E_CUDA;
+    cudaStream_t s;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return F3D_E_CUDA;
+    const size_t P = (size_t)h * w, nb_img = P * c * 4, nb_dep = P * 4, nb_v = (size_t)nver * 12, nb_t = (size_t)ntri * 12,
+                 nb_c = (size_t)nver * c * 4, nb_ws = f3d_workspace_bytes(ntri, h, w);
+    void *d_img = nullptr, *d_dep = nullptr, *d_v = nullptr, *d_t = nullptr, *d_c = nullptr, *d_ws = nullptr;
+    int rc = F3D_E_CUDA;
+    if (cudaMallocAsync(&d_img, nb_img, s) == cudaSuccess && cudaMallocAsync(&d_dep, nb_dep, s) == cudaSuccess &&
+        cudaMallocAsync(&d_v, nb_v, s) == cudaSuccess && cudaMallocAsync(&d_t, nb_t, s) == cudaSuccess &&
+        cudaMallocAsync(&d_c, nb_c, s) == cudaSuccess && cudaMallocAsync(&d_ws, nb_ws, s) == cudaSuccess &&
+        cudaMemcpyAsync(d_img, image, nb_img, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+        cudaMemcpyAsync(d_dep, depth_buffer, nb_dep, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+        cudaMemcpyAsync(d_v, vertices, nb_v, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+        cudaMemcpyAsync(d_t, triangles, nb_t, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+        cudaMemcpyAsync(d_c, colors, nb_c, cudaMemcpyHostToDevice, s) == cudaSuccess) {
+        rc = f3d_run((float*)d_img, nullptr, false, (const float*)d_v, (const int32_t*)d_t, (const float*)d_c, (float*)d_dep, 0.f,
+                     nver, ntri, h, w, c, d_ws, nb_ws, s);
+        if (rc == F3D_OK && (cudaMemcpyAsync(image, d_img, nb_img, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                             cudaMemcpyAsync(depth_buffer, d_dep, nb_dep, cudaMemcpyDeviceToHost, s) != cudaSuccess)) rc = F3D_E_CUDA;
+    }
+    void* all[] = {d_img, d_dep, d_v, d_t, d_c, d_ws};
+    for (void* q : all) if (q) cudaFreeAsync(q, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) rc = F3D_E_CUDA;
+    cudaStreamDestroy(s);
+    return rc;
 }
 
 extern "C" int f3d_image_to_u8(const float* image, uint8_t* out_u8, int64_t count, gs_stream_t stream)

@@ -45,6 +45,26 @@ def render_colors_device(image, vertices, triangles, colors, depth_buffer, h, w,
     return workspace
 
 
+def bake_colors_device(vertices, triangles, colors, h, w, c, u8=False, depth_init=-999999.0, workspace=None):
+    """face3d/mesh/render.py:52-86 as one device pass: fresh image (every pixel written: winner colour or 0), private constant
+    depth.  Returns a [h,w,c] float32 (or uint8 = (value*255) truncated, helpers.py:959) CUDA tensor."""
+    L = _lib.lib()
+    dev = vertices.device
+    ntri, nver = int(triangles.shape[0]), int(vertices.shape[0])
+    need = L.f3d_workspace_bytes(ntri, h, w)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    out = torch.empty((h, w, c), dtype=torch.uint8 if u8 else torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        code = L.f3d_bake_colors(None if u8 else C.c_void_p(out.data_ptr()), C.c_void_p(out.data_ptr()) if u8 else None,
+                                 C.c_void_p(vertices.data_ptr()), C.c_void_p(triangles.data_ptr()), C.c_void_p(colors.data_ptr()),
+                                 float(depth_init), nver, ntri, int(h), int(w), int(c), C.c_void_p(workspace.data_ptr()),
+                                 workspace.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if code != 0:
+        raise RuntimeError(f"f3d_bake_colors failed with code {code}")
+    return out
+
+
 def image_to_u8_device(image: torch.Tensor) -> torch.Tensor:
     """(image*255).astype(uint8) of helpers.py:959 on the device."""
     out = torch.empty(image.shape, dtype=torch.uint8, device=image.device)
@@ -64,13 +84,11 @@ def render_colors_core(image, vertices, triangles, colors, depth_buffer, nver, n
     _check("depth_buffer", depth_buffer, np.float32, 2)
     if not torch.cuda.is_available():
         raise RuntimeError("topo4d_b200.face3d_compat: CUDA device required (there is no CPU path)")
-    dev = torch.device(device)
-    d_img = torch.from_numpy(image).to(dev, non_blocking=True)
-    d_dep = torch.from_numpy(depth_buffer).to(dev, non_blocking=True)
-    d_v = torch.from_numpy(vertices[:nver]).to(dev)
-    d_t = torch.from_numpy(triangles[:ntri]).to(dev)
-    d_c = torch.from_numpy(colors[:nver]).to(dev)
-    render_colors_device(d_img, d_v, d_t, d_c, d_dep, h, w, c)
-    image[...] = d_img.cpu().numpy()
-    depth_buffer[...] = d_dep.cpu().numpy()
+    # the C-ABI host-pointer entry does the copies, the kernels and the in-place update (f3d_render_colors_host)
+    with torch.cuda.device(torch.device(device)):
+        code = _lib.lib().f3d_render_colors_host(C.c_void_p(image.ctypes.data), C.c_void_p(vertices.ctypes.data),
+                                                 C.c_void_p(triangles.ctypes.data), C.c_void_p(colors.ctypes.data),
+                                                 C.c_void_p(depth_buffer.ctypes.data), int(nver), int(ntri), int(h), int(w), int(c))
+    if code != 0:
+        raise RuntimeError(f"f3d_render_colors_host failed with code {code}")
     return None

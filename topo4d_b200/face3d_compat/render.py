@@ -8,22 +8,37 @@ import torch
 from . import mesh_core_cython
 
 
-def _device_render(vertices, triangles, colors, h, w, c, BG, device):
-    """Uploads the mesh, initialises image / depth ON THE DEVICE (zeros or BG, -999999) and rasterizes.
-    The reference allocates and casts on the host (render.py:66-77); values are identical."""
+def _upload(vertices, triangles, colors, device):
     dev = torch.device(device)
     if not torch.cuda.is_available():
         raise RuntimeError("topo4d_b200.face3d_compat: CUDA device required (there is no CPU path)")
     d_v = torch.from_numpy(np.ascontiguousarray(vertices, dtype=np.float32)).to(dev)
     d_t = torch.from_numpy(np.ascontiguousarray(triangles, dtype=np.int32)).to(dev)
     d_c = torch.from_numpy(np.ascontiguousarray(colors, dtype=np.float32)).to(dev)
+    return dev, d_v, d_t, d_c
+
+
+def _device_render(vertices, triangles, colors, h, w, c, BG, device, u8=False):
+    """Uploads the mesh and rasterizes ON THE DEVICE.  Without BG this is the fused bake (fresh image, private constant depth:
+    nothing but the result is written); with BG the caller's image is painted into, with a -999999 depth plane like the
+    reference's (render.py:66-77); values are identical."""
+    dev, d_v, d_t, d_c = _upload(vertices, triangles, colors, device)
     if BG is None:
-        d_img = torch.zeros((h, w, c), dtype=torch.float32, device=dev)
-    else:
-        d_img = torch.from_numpy(BG).to(dev)
+        return mesh_core_cython.bake_colors_device(d_v, d_t, d_c, h, w, c, u8=u8)
+    d_img = torch.from_numpy(BG).to(dev)
     d_dep = torch.full((h, w), -999999.0, dtype=torch.float32, device=dev)
     mesh_core_cython.render_colors_device(d_img, d_v, d_t, d_c, d_dep, h, w, c)
-    return d_img
+    return mesh_core_cython.image_to_u8_device(d_img) if u8 else d_img
+
+
+def _to_host(d_img: torch.Tensor) -> np.ndarray:
+    """Device result -> NumPy array in page-locked memory from PyTorch's caching host allocator: the copy runs at PCIe speed
+    and, from the second bake on, the 805 MB block is reused -- no page faults of a fresh np.empty, no pageable staging.  The
+    block returns to the cache when the array is garbage-collected."""
+    host = torch.empty(d_img.shape, dtype=d_img.dtype, pin_memory=True)
+    host.copy_(d_img, non_blocking=True)
+    torch.cuda.current_stream(d_img.device).synchronize()
+    return host.numpy()
 
 
 def render_colors(vertices, triangles, colors, h, w, c=3, BG=None, device="cuda"):
@@ -40,21 +55,16 @@ def render_colors(vertices, triangles, colors, h, w, c=3, BG=None, device="cuda"
         image: [h, w, c] float32
     '''
     if BG is None:
-        image = np.empty((h, w, c), dtype=np.float32)
-    else:
-        assert BG.shape[0] == h and BG.shape[1] == w and BG.shape[2] == c
-        if BG.dtype != np.float32 or not BG.flags.c_contiguous:
-            raise ValueError("Buffer dtype mismatch, expected 'float32' C-contiguous BG")   # as the typed Cython arg would
-        image = BG
+        return _to_host(_device_render(vertices, triangles, colors, h, w, c, None, device))
+    assert BG.shape[0] == h and BG.shape[1] == w and BG.shape[2] == c
+    if BG.dtype != np.float32 or not BG.flags.c_contiguous:
+        raise ValueError("Buffer dtype mismatch, expected 'float32' C-contiguous BG")   # as the typed Cython arg would
     d_img = _device_render(vertices, triangles, colors, h, w, c, BG, device)
-    torch.from_numpy(image).copy_(d_img)                 # one D2H straight into the array that is returned
-    return image
+    torch.from_numpy(BG).copy_(d_img)                    # painted INTO the caller's array, like the reference (render.py:70-71)
+    return BG
 
 
 def render_colors_u8(vertices, triangles, colors, h, w, c=3, device="cuda"):
     """The whole write_texture body up to imsave (helpers.py:956-959): render, `*255`, astype(uint8) -- on the
     device, so only h*w*c bytes cross PCIe instead of 4x that."""
-    d_img = _device_render(vertices, triangles, colors, h, w, c, None, device)
-    out = np.empty((h, w, c), dtype=np.uint8)
-    torch.from_numpy(out).copy_(mesh_core_cython.image_to_u8_device(d_img))
-    return out
+    return _to_host(_device_render(vertices, triangles, colors, h, w, c, None, device, u8=True))
