@@ -115,6 +115,13 @@ def main():
     ap.add_argument("--graph", action="store_true", help="one CUDA graph per camera for the whole iteration (single rank only)")
     ap.add_argument("--torch-activations", action="store_true", help="helpers.py:91-112 as PyTorch ops instead of the fused kernel")
     ap.add_argument("--json", default="")
+    ap.add_argument("--scale-iters", action="store_true", help="G ranks: ceil(iters / G) steps per frame, so the VIEWS SEEN per frame stay "
+                    "what the one-view-per-step loop sees (gradients are the mean over the G views of a step)")
+    ap.add_argument("--files", default="", help="directory: the ground-truth sequence is written there as JPEG files (rank 0, if absent) in the "
+                    "reference's layout <dir>/seq/%%06d/<cam>.jpg and read back through topo4d_b200.frames.FramePrefetcher (GPU decode, "
+                    "one frame ahead) instead of being handed over as tensors")
+    ap.add_argument("--save-means", default="", help="npy file: final means3D of every frame [frames, N, 3] (rank 0)")
+    ap.add_argument("--compare-with", default="", help="npy file written by --save-means of another run (e.g. G = 1): report the distance")
     a = ap.parse_args()
     global FUSED_ACTIVATIONS
     FUSED_ACTIVATIONS = not a.torch_activations
@@ -155,12 +162,34 @@ def main():
     uv_v, uv_t, _ = synth.uv_grid_mesh(grid=64, res=max(a.bake, 64), seed=0, extras=False) if a.bake else (None, None, None)
 
     gen = torch.Generator().manual_seed(0)                   # the same view order on every rank
-    report = {"world": world, "frames": [], "config": vars(a)}
+    iters = -(-a.iters // world) if a.scale_iters else a.iters
+    report = {"world": world, "frames": [], "config": vars(a), "steps_per_frame": iters, "views_per_step": world,
+              "views_seen_per_frame": iters * world,
+              "semantics": "G ranks render G different views per optimiser step (rank r takes order[r] of a fresh permutation), gradients are "
+                           "AVERAGED over the G views with one all-reduce, every rank applies the same Adam step; --scale-iters divides the "
+                           "steps per frame by G so the views seen per frame match the reference's one-view-per-step loop (train.py:661-673)"}
+    prefetch = None
+    if a.files:
+        from torchvision.io import encode_jpeg
+        from topo4d_b200 import frames as fr
+        seq_dir = os.path.join(a.files, "seq")
+        if rank == 0 and not os.path.exists(os.path.join(seq_dir, "%06d" % a.frames)):
+            for t in range(a.frames):                        # write the synthetic sequence once, like a capture session on disk
+                gt_t["means3D"] = deform(means0, float(t))
+                d = os.path.join(seq_dir, "%06d" % (t + 1))
+                os.makedirs(d, exist_ok=True)
+                for k, im in enumerate(render_gt(gt_t, cams, dev)):
+                    open(os.path.join(d, "cam%02d.jpg" % k), "wb").write(
+                        encode_jpeg((im * 255).round().to(torch.uint8).cpu(), quality=95).numpy().tobytes())
+        if world > 1:
+            dist.barrier()
+        prefetch = fr.FramePrefetcher(lambda t: fr.list_frame_files(a.files, "seq", t + 1), [0] * a.views, dev, num_frames=a.frames)
+    saved = []
     t_start = time.perf_counter()
     steps_total = 0
     for t in range(a.frames):
         gt_t["means3D"] = deform(means0, float(t))
-        gts = render_gt(gt_t, cams, dev)
+        gts = prefetch.get(t) if prefetch else render_gt(gt_t, cams, dev)
         if a.graph:
             for k in range(a.views):
                 gt_static[k].copy_(gts[k])                   # graphs read static buffers: new frame, same storage
@@ -171,7 +200,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         first = last = None
-        for i in range(a.iters):
+        for i in range(iters):
             order = torch.randperm(a.views, generator=gen).tolist()
             cam_id = order[rank % a.views] if world > 1 else order[0]
             if a.graph:
@@ -206,7 +235,9 @@ def main():
             geo = float((params["means3D"][~static_mask] - gt_t["means3D"][~static_mask]).norm(dim=1).mean())
             pinned = float((params["means3D"][static_mask] - means0[static_mask]).abs().max())
         frame = {"frame": t, "loss_first": float(first), "loss_last": float(last), "psnr_db": p, "mean_vertex_err_m": geo,
-                 "pinned_rows_max_dev": pinned, "ms_per_step": e0.elapsed_time(e1) / a.iters}
+                 "pinned_rows_max_dev": pinned, "ms_per_step": e0.elapsed_time(e1) / iters}
+        if a.save_means or a.compare_with:
+            saved.append(params["means3D"].detach().cpu().numpy().copy())
         if a.bake and rank == 0:                             # texture bake of the learnt colours (helpers.py:953-960)
             tb = time.perf_counter()
             col = params["rgb_colors"].detach().clamp(0, 1).cpu().numpy().astype(np.float64)
@@ -219,6 +250,19 @@ def main():
             print(json.dumps(frame), flush=True)
     report["steps_per_s"] = steps_total / (time.perf_counter() - t_start)
     report["views_per_s"] = report["steps_per_s"] * world
+    report["seconds_total"] = time.perf_counter() - t_start
+    report["final_mean_vertex_err_m"] = report["frames"][-1]["mean_vertex_err_m"]
+    report["mean_over_frames_vertex_err_m"] = float(np.mean([f["mean_vertex_err_m"] for f in report["frames"][1:] or report["frames"]]))
+    if rank == 0 and a.save_means:
+        np.save(a.save_means, np.stack(saved))
+    if rank == 0 and a.compare_with and os.path.exists(a.compare_with):
+        other = np.load(a.compare_with)
+        n = min(len(other), len(saved))
+        dist_m = np.linalg.norm(np.stack(saved)[:n] - other[:n], axis=-1)                # [frames, N]
+        report["vs_other_run"] = {"file": a.compare_with, "frames_compared": int(n), "mean_vertex_distance_m": float(dist_m.mean()),
+                                  "max_vertex_distance_m": float(dist_m.max()), "final_frame_mean_m": float(dist_m[-1].mean()),
+                                  "deformation_amplitude_m": 0.004,
+                                  "note": "distance between the meshes of this run and of the other run, per frame and vertex"}
     if rank == 0:
         print(json.dumps({k: v for k, v in report.items() if k != "frames"}), flush=True)
         if a.json:
