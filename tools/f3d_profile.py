@@ -1,4 +1,5 @@
-"""Tiny driver for ncu: one warm-up + one timed 8192^2 bake (device tensors only)."""
+"""Tiny driver for ncu: warm-up + one 8192^2 bake (device tensors only): the fused bake path and the in-place API path.
+    ncu --set full --clock-control none -k regex:f3d -c 12 -o gpurun_out/f3d python tools/f3d_profile.py [grid]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,8 +10,6 @@ res = 8192
 v, t, c = synth.uv_grid_mesh(grid=grid, res=res, seed=0)
 dev = torch.device("cuda:0")
 d_v = torch.tensor(v, dtype=torch.float32, device=dev); d_t = torch.tensor(t, dtype=torch.int32, device=dev); d_c = torch.tensor(c, dtype=torch.float32, device=dev)
-ws = None
 for _ in range(2):
-    img = torch.zeros((res, res, 3), device=dev); dep = torch.full((res, res), -999999.0, device=dev)
-    ws = mcc.render_colors_device(img, d_v, d_t, d_c, dep, res, res, 3, ws)
+    out = mcc.bake_colors_device(d_v, d_t, d_c, res, res, 3)
 torch.cuda.synchronize()

@@ -27,23 +27,38 @@ struct Tri {
     int xmin, xmax, ymin, ymax;
 };
 
-// reference get_point_weight / isPointInTri arithmetic (mesh_core.cpp:23-82), op for op
-__device__ __forceinline__ void bary(float px, float py, const Tri& t, float& w0, float& w1, float& w2, bool& inside)
+// reference get_point_weight / isPointInTri arithmetic (mesh_core.cpp:23-82), op for op.  The part that does not depend on the
+// pixel (edge vectors, their dot products, the inverse Gram determinant) is computed once per triangle (TriSetup); the per-pixel
+// part repeats the reference's remaining operations in the reference's order, so the bits are those of the fused function.
+struct TriSetup { float v0x, v0y, v1x, v1y, dot00, dot01, dot11, inv; };
+
+__device__ __forceinline__ TriSetup tri_setup(const Tri& t)
 {
-    const float v0x = t.x2 - t.x0, v0y = t.y2 - t.y0;
-    const float v1x = t.x1 - t.x0, v1y = t.y1 - t.y0;
+    TriSetup s;
+    s.v0x = t.x2 - t.x0; s.v0y = t.y2 - t.y0;
+    s.v1x = t.x1 - t.x0; s.v1y = t.y1 - t.y0;
+    s.dot00 = s.v0x * s.v0x + s.v0y * s.v0y;
+    s.dot01 = s.v0x * s.v1x + s.v0y * s.v1y;
+    s.dot11 = s.v1x * s.v1x + s.v1y * s.v1y;
+    const float den = s.dot00 * s.dot11 - s.dot01 * s.dot01;
+    s.inv = (den == 0.0f) ? 0.0f : 1.0f / den;
+    return s;
+}
+
+__device__ __forceinline__ void bary_px(float px, float py, const Tri& t, const TriSetup& s, float& w0, float& w1, float& w2, bool& inside)
+{
     const float v2x = px - t.x0, v2y = py - t.y0;
-    const float dot00 = v0x * v0x + v0y * v0y;
-    const float dot01 = v0x * v1x + v0y * v1y;
-    const float dot02 = v0x * v2x + v0y * v2y;
-    const float dot11 = v1x * v1x + v1y * v1y;
-    const float dot12 = v1x * v2x + v1y * v2y;
-    const float den = dot00 * dot11 - dot01 * dot01;
-    const float inv = (den == 0.0f) ? 0.0f : 1.0f / den;
-    const float u = (dot11 * dot02 - dot01 * dot12) * inv;
-    const float v = (dot00 * dot12 - dot01 * dot02) * inv;
+    const float dot02 = s.v0x * v2x + s.v0y * v2y;
+    const float dot12 = s.v1x * v2x + s.v1y * v2y;
+    const float u = (s.dot11 * dot02 - s.dot01 * dot12) * s.inv;
+    const float v = (s.dot00 * dot12 - s.dot01 * dot02) * s.inv;
     inside = (u >= 0.0f) && (v >= 0.0f) && (u + v < 1.0f);
     w0 = 1.0f - u - v; w1 = v; w2 = u;
+}
+
+__device__ __forceinline__ void bary(float px, float py, const Tri& t, float& w0, float& w1, float& w2, bool& inside)
+{
+    bary_px(px, py, t, tri_setup(t), w0, w1, w2, inside);
 }
 
 __device__ __forceinline__ bool accepts(int x, int y, int h, int w, bool inside)
@@ -86,11 +101,11 @@ __device__ __forceinline__ bool load_tri(const float* __restrict__ vertices, con
 //   STAGE 1  imax[pix] = max (~index) over the accepting triangles whose depth equals dmax[pix]
 // (the r01 kernel used one 64-bit atomicMax on depth << 32 | ~index: twice the key traffic, half the atomic rate)
 template <int STAGE>
-__device__ __forceinline__ void test_pixel(const Tri& t, int idx, int x, int y, int h, int w, int y_lo, bool flat,
+__device__ __forceinline__ void test_pixel(const Tri& t, const TriSetup& ts, int idx, int x, int y, int h, int w, int y_lo, bool flat,
                                            unsigned* __restrict__ dmax, unsigned* __restrict__ imax)
 {
     float w0, w1, w2; bool inside;
-    bary((float)x, (float)y, t, w0, w1, w2, inside);
+    bary_px((float)x, (float)y, t, ts, w0, w1, w2, inside);
     if (!accepts(x, y, h, w, inside)) return;
     const float d = w0 * t.z0 + w1 * t.z1 + w2 * t.z2;
     if (d != d) return;                                      // NaN never passes '>' in the reference
@@ -119,8 +134,9 @@ f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ trian
         int bw = 0, area = 0;
         if (ok) { bw = t.xmax - t.xmin + 1; const long long a = (long long)bw * (t.ymax - t.ymin + 1); area = a > 0x7fffffffLL ? 0x7fffffff : (int)a; }
         if (ok && area <= SMALL_BOX) {
+            const TriSetup ts = tri_setup(t);
             for (int y = t.ymin; y <= t.ymax; y++)
-                for (int x = t.xmin; x <= t.xmax; x++) test_pixel<STAGE>(t, i, x, y, h, w, y_lo, flat, dmax, imax);
+                for (int x = t.xmin; x <= t.xmax; x++) test_pixel<STAGE>(t, ts, i, x, y, h, w, y_lo, flat, dmax, imax);
         }
         unsigned big = __ballot_sync(0xffffffffu, ok && area > SMALL_BOX);
         while (big) {
@@ -134,11 +150,12 @@ f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ trian
             const int sbw = __shfl_sync(0xffffffffu, bw, src);
             const int sarea = __shfl_sync(0xffffffffu, area, src);
             const int sidx = (int)base + src;
+            const TriSetup ts = tri_setup(s);                  // once per triangle (every lane computes the same values)
             // lanes walk the box in row-major order, 32 pixels per step; (xx, yy) advance incrementally (no division)
             int xx = lane, yy = 0;
             while (xx >= sbw) { xx -= sbw; yy++; }
             for (int k = lane; k < sarea; k += 32) {
-                test_pixel<STAGE>(s, sidx, s.xmin + xx, s.ymin + yy, h, w, y_lo, flat, dmax, imax);
+                test_pixel<STAGE>(s, ts, sidx, s.xmin + xx, s.ymin + yy, h, w, y_lo, flat, dmax, imax);
                 xx += 32;
                 while (xx >= sbw) { xx -= sbw; yy++; }
             }

@@ -49,6 +49,8 @@ static int validate(const GsProblem* p)
             if (p->sh_coeffs < (p->sh_degree + 1) * (p->sh_degree + 1)) return GS_E_BAD_ARGS;
         }
     }
+    // the kernels read rotations (and write their gradient) as 16-byte vectors
+    if (p->N > 0 && p->rotations && ((uintptr_t)p->rotations & 15u) != 0) return GS_E_BAD_ARGS;
     if (p->workspace_bytes < gs_workspace_bytes(p->N, p->V, p->H, p->W, p->cap_instances)) return GS_E_WORKSPACE_SMALL;
     if (((uintptr_t)p->workspace & 255u) != 0) return GS_E_BAD_ARGS;
     return 0;
@@ -162,6 +164,7 @@ extern "C" int gs_backward_stages(const GsProblem* p, const GsBackwardIO* io, ui
     if (!io->radii || !io->dL_dmeans3D || !io->dL_dmeans2D || !io->dL_dopacities) return GS_E_BAD_ARGS;
     if (p->shs ? !io->dL_dshs : !io->dL_dcolors) return GS_E_BAD_ARGS;
     if (p->cov3D_precomp ? !io->dL_dcov3D : (!io->dL_dscales || !io->dL_drotations)) return GS_E_BAD_ARGS;
+    if (io->dL_drotations && ((uintptr_t)io->dL_drotations & 15u) != 0) return GS_E_BAD_ARGS;       // written as float4
     cudaStream_t s = (cudaStream_t)stream;
     const GsLayout L = gs_make_layout(p->N, p->V, p->H, p->W, p->cap_instances);
     const GsParams q = make_params(p, L);
@@ -237,7 +240,7 @@ extern "C" const char* gs_last_error(int code)
 {
     switch (code) {
         case GS_OK: return "ok";
-        case GS_E_BAD_ARGS: return "bad arguments (NULL/inconsistent pointers, sizes, or not exactly one of shs|colors_precomp / (scales,rotations)|cov3D_precomp)";
+        case GS_E_BAD_ARGS: return "bad arguments (NULL/inconsistent pointers, sizes, rotations / dL_drotations not 16-byte aligned, or not exactly one of shs|colors_precomp / (scales,rotations)|cov3D_precomp)";
         case GS_E_WORKSPACE_SMALL: return "workspace smaller than gs_workspace_bytes()";
         case GS_E_CUDA: return "CUDA runtime error (see gs_last_cuda_error)";
         case GS_E_OVERFLOW: return "instance capacity exceeded: grow cap_instances to status.num_instances and retry";

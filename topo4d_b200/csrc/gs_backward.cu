@@ -120,7 +120,7 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
             const float gr[3] = {(cl & 1u) ? 0.f : a2.x, (cl & 2u) ? 0.f : a2.y, (cl & 4u) ? 0.f : a2.z};
             const float* __restrict__ sh = p.shs + (size_t)i * p.M * 3;
             float gdx = 0.f, gdy = 0.f, gdz = 0.f;
-            if (((p.M * 3) & 3) == 0 && (KK * 3) % 4 == 0) {
+            if (((p.M * 3) & 3) == 0 && (KK * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(p.shs) & 15) == 0) {
                 const float4* __restrict__ sh4 = reinterpret_cast<const float4*>(sh);
                 #pragma unroll
                 for (int q4 = 0; q4 < (KK * 3) / 4; q4++) {

@@ -468,12 +468,28 @@ __global__ void __launch_bounds__(SORT_LONG_THREADS, 1) sort_gather_long_kernel(
 
 void gs_launch_tile_scan(const GsParams& p, int num_sms, cudaStream_t s)
 {
-    if (p.scan_blocks <= num_sms) {             // whole grid co-resident: one launch (see scan_write_kernel<true>)
-        scan_write_kernel<true><<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
-    } else {
-        scan_reduce_kernel<<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
-        scan_write_kernel<false><<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
+    // FUSED = one launch whose blocks meet at a grid-wide counter: only legal when the whole grid is co-resident.  A single
+    // block needs no barrier; several blocks are launched COOPERATIVELY, which makes the runtime guarantee co-residency (or
+    // refuse: MPS / green-context SM limits, other persistent kernels holding the SMs) instead of assuming it from the SM count;
+    // anything else takes the two-launch path.
+    if (p.scan_blocks == 1) { scan_write_kernel<true><<<1, SCAN_THREADS, 0, s>>>(p); return; }
+    static thread_local int coop_blocks = -1, coop_sms = 0;
+    if (coop_blocks < 0 || coop_sms != num_sms) {
+        int dev = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)scan_write_kernel<true>, SCAN_THREADS, 0) != cudaSuccess) per_sm = 0;
+        coop_blocks = per_sm * num_sms;
+        coop_sms = num_sms;
     }
+    if (p.scan_blocks <= coop_blocks) {
+        GsParams q = p;
+        void* args[] = {(void*)&q};
+        if (cudaLaunchCooperativeKernel((const void*)scan_write_kernel<true>, dim3(p.scan_blocks), dim3(SCAN_THREADS), args, 0, s) == cudaSuccess) return;
+        (void)cudaGetLastError();                  // refused (resources held elsewhere): fall through to the two-launch path
+    }
+    scan_reduce_kernel<<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
+    scan_write_kernel<false><<<p.scan_blocks, SCAN_THREADS, 0, s>>>(p);
 }
 
 void gs_launch_sort_gather(const GsParams& p, int num_sms, cudaStream_t s)

@@ -7,6 +7,7 @@ one view per call -- train.py:307 -- which is V = 1).
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -35,12 +36,17 @@ _PINNED_RING = None                # one pinned allocation, 256 status slots han
 _PINNED_NEXT = 0
 
 
+_LOCK = threading.Lock()            # guards the pinned ring cursor; the memo dictionaries are keyed per device and only ever
+                                    # updated with single dict stores (atomic under the GIL)
+
+
 def _pinned_slot() -> torch.Tensor:
     global _PINNED_RING, _PINNED_NEXT
-    if _PINNED_RING is None:
-        _PINNED_RING = torch.empty(256 * 64, dtype=torch.uint8).pin_memory()
-    i = _PINNED_NEXT
-    _PINNED_NEXT = (i + 1) % 256
+    with _LOCK:
+        if _PINNED_RING is None:
+            _PINNED_RING = torch.empty(256 * 64, dtype=torch.uint8).pin_memory()
+        i = _PINNED_NEXT
+        _PINNED_NEXT = (i + 1) % 256
     return _PINNED_RING[i * 64:i * 64 + ctypes_sizeof_status_dev]
 
 
@@ -60,8 +66,12 @@ def _f32c(t: torch.Tensor | None, dev) -> torch.Tensor | None:
     if t is None:
         return None
     if t.dtype is torch.float32 and t.device == dev:
-        return t if t.is_contiguous() else t.contiguous()
-    return t.to(device=dev, dtype=torch.float32).contiguous()
+        t = t if t.is_contiguous() else t.contiguous()
+    else:
+        t = t.to(device=dev, dtype=torch.float32).contiguous()
+    # the kernels use 16-byte vector loads on per-Gaussian rows (rotations, SH): a contiguous slice of a flat parameter buffer
+    # at an offset that is not a multiple of four floats would fault with a sticky 'misaligned address'
+    return t.clone() if (t.data_ptr() & 15) and t.numel() else t
 
 
 def pack_cameras_numpy(cams, bg=(0.0, 0.0, 0.0)) -> np.ndarray:

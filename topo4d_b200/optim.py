@@ -24,7 +24,9 @@ class FusedAdam(torch.optim.Optimizer):
         if lr < 0.0 or eps < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
-        self._pins: dict[int, tuple[torch.Tensor, torch.Tensor | None]] = {}
+        # id(param) -> (weak reference to the parameter, mask, values): the weak reference proves at look-up time that the id
+        # still belongs to the tensor the pin was registered for (an id can be reused after a tensor is freed)
+        self._pins: dict[int, tuple] = {}
         # capturable=True: step counters and learning rates live on the device, so a step() captured in a CUDA graph
         # (topo4d_b200.graph.capture) advances correctly at every replay; after editing param_groups[i]['lr']
         # (update_optimizer, helpers.py:801-804) call sync_hyperparams() -- no re-capture needed.
@@ -42,9 +44,27 @@ class FusedAdam(torch.optim.Optimizer):
             self._pins.pop(id(param), None)
             return
         rows = param.shape[0]
+        if mask.numel() != rows:
+            raise ValueError(f"pin(): mask has {mask.numel()} entries, the parameter has {rows} rows")
         m = mask.to(device=param.device).reshape(rows).to(torch.uint8).contiguous()
         v = None if values is None else values.to(device=param.device, dtype=torch.float32).expand_as(param).contiguous()
-        self._pins[id(param)] = (m, v)
+        import weakref
+        self._pins[id(param)] = (weakref.ref(param), m, v)
+
+    def pin_compact(self, param: torch.Tensor, overwrites) -> None:
+        """The reference's own form (train.py:676-699): an ORDERED list of ``(mask, values)`` statements
+        ``params[name][mask] = values`` where `values` is a scalar, a row, or the compact ``[mask.sum(), ...]`` tensor boolean
+        indexing takes.  They are merged, in order (later statements win), into the one full-shape mask / value table pin() holds."""
+        rows = param.shape[0]
+        full_m = torch.zeros(rows, dtype=torch.bool, device=param.device)
+        full_v = torch.zeros_like(param, dtype=torch.float32)
+        for mask, values in overwrites:
+            mb = mask.to(device=param.device)
+            if mb.dtype is not torch.bool:                       # index arrays, like the reference's region masks
+                mb = torch.zeros(rows, dtype=torch.bool, device=param.device).index_fill_(0, mb.long().reshape(-1), True)
+            full_v[mb] = values if not torch.is_tensor(values) else values.to(device=param.device, dtype=torch.float32)
+            full_m |= mb
+        self.pin(param, full_m, full_v)
 
     def sync_hyperparams(self) -> None:
         """Capturable mode: push the groups' current learning rates to their device slots (one small H2D copy)."""
@@ -85,7 +105,7 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 step_dev = lr_dev = None
                 if self.capturable:
-                    if self._lr_dev is None:
+                    if self._lr_dev is None or self._lr_dev.numel() != len(self.param_groups):      # add_param_group grows it
                         if capturing:
                             raise RuntimeError("run at least one eager step() before capturing")
                         self._lr_dev = torch.zeros(len(self.param_groups), dtype=torch.float32, device=p.device)
@@ -96,6 +116,14 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = int(st["step"]) + 1
                     step_host = st["step"]
                 pin = self._pins.get(id(p))
+                if pin is not None:
+                    if pin[0]() is not p:                        # stale entry of a freed tensor whose id was reused
+                        del self._pins[id(p)]
+                        pin = None
+                    else:
+                        pin = pin[1:]
+                        if pin[0].numel() != p.shape[0] or (pin[1] is not None and pin[1].shape != p.shape):
+                            raise RuntimeError("FusedAdam: a pinned parameter changed shape; register the pin again")
                 rw = int(p.numel() // p.shape[0]) if (pin is not None and p.dim() > 0 and p.shape[0] > 0) else 1
                 segs.append(_lib.T4dAdamSegment(p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                                                 None if pin is None else pin[0].data_ptr(),

@@ -11,6 +11,7 @@ Adds ``render_views`` -- the same op over V cameras in one launch sequence (view
 from __future__ import annotations
 
 import os
+import threading
 from collections import OrderedDict
 from typing import NamedTuple
 
@@ -38,6 +39,8 @@ class GaussianRasterizationSettings(NamedTuple):
 
 _CAM_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 _CAM_CACHE_MAX = 256
+_CAM_LOCK = threading.Lock()          # one thread per GPU is a supported deployment: shared caches are locked,
+                                      # per-call bookkeeping (_PENDING, _CAPTURE_LOG) is thread-local
 
 
 def pack_settings(rs: GaussianRasterizationSettings) -> torch.Tensor:
@@ -46,19 +49,21 @@ def pack_settings(rs: GaussianRasterizationSettings) -> torch.Tensor:
     tens = (rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg)
     key = tuple((t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride())) for t in tens) + \
         (float(rs.tanfovx), float(rs.tanfovy))
-    hit = _CAM_CACHE.get(key)
-    if hit is not None:
-        _CAM_CACHE.move_to_end(key)
-        return hit[0]
+    with _CAM_LOCK:
+        hit = _CAM_CACHE.get(key)
+        if hit is not None:
+            _CAM_CACHE.move_to_end(key)
+            return hit[0]
     dev = rs.viewmatrix.device
     f = lambda t, n: t.to(device=dev, dtype=torch.float32).reshape(-1)[:n]
     tail = torch.zeros(GS_CAM_FLOATS - 38, dtype=torch.float32)
     tail[0], tail[1] = float(rs.tanfovx), float(rs.tanfovy)
     packed = torch.cat([f(rs.viewmatrix.contiguous(), 16), f(rs.projmatrix.contiguous(), 16), f(rs.campos, 3), f(rs.bg, 3),
                         tail.to(dev)]).contiguous()
-    _CAM_CACHE[key] = (packed, tens)         # keep the source tensors alive so data_ptr keys stay unique
-    if len(_CAM_CACHE) > _CAM_CACHE_MAX:
-        _CAM_CACHE.popitem(last=False)
+    with _CAM_LOCK:
+        _CAM_CACHE[key] = (packed, tens)     # keep the source tensors alive so data_ptr keys stay unique
+        if len(_CAM_CACHE) > _CAM_CACHE_MAX:
+            _CAM_CACHE.popitem(last=False)
     return packed
 
 
@@ -66,10 +71,37 @@ def pack_settings(rs: GaussianRasterizationSettings) -> torch.Tensor:
 # host sync upstream does for `num_rendered` -- and transparently re-run if the instance capacity overflowed.
 # TOPO4D_B200_SYNC=0: fully asynchronous forward; the status of call k is checked at call k+1 (by then it is
 # long complete, so the check is free) and an overflow raises there after growing the capacity for the retry.
-_PENDING: list = []
+class _PerThread(threading.local):
+    def __init__(self):
+        self.pending: list = []
+        self.capture_log: list = []
+
+
+_TLS = _PerThread()
+
+
+class _ListProxy:
+    """Module-level name for a thread-local list (`rasterizer._PENDING`, `rasterizer._CAPTURE_LOG`)."""
+    def __init__(self, attr):
+        self._attr = attr
+
+    def _l(self):
+        return getattr(_TLS, self._attr)
+
+    def append(self, x): self._l().append(x)
+    def pop(self): return self._l().pop()
+    def clear(self): self._l().clear()
+    def __len__(self): return len(self._l())
+    def __bool__(self): return bool(self._l())
+    def __iter__(self): return iter(list(self._l()))
+    def __delitem__(self, k): del self._l()[k]
+    def __getitem__(self, k): return self._l()[k]
+
+
+_PENDING = _ListProxy("pending")
 # Forwards issued while the current stream is being captured into a CUDA graph cannot touch the host at all: they run
 # with check="none" and their states are logged here so that topo4d_b200.graph.capture can verify them after replays.
-_CAPTURE_LOG: list = []
+_CAPTURE_LOG = _ListProxy("capture_log")
 
 
 def _sync_mode() -> bool:
