@@ -47,9 +47,10 @@ def test_workspace_bytes_arithmetic():
     assert per_view >= 1080 * 1920 * 8 + 60000 * 97                  # final_T + n_contrib + geom + grad2d + clamp
     assert L.gs_workspace_bytes(-1, 1, 8, 8, 0) == 0 and L.gs_workspace_bytes(1, 0, 8, 8, 0) == 0
     # face3d: header + two u32 key planes for one band of rows (<= 1 GiB per plane: the whole image at 8192^2)
-    assert L.f3d_workspace_bytes(10, 8192, 8192) == 256 + 2 * 8192 * 8192 * 4
-    assert L.f3d_workspace_bytes(10, 32768, 32768) == 256 + 2 * 8192 * 32768 * 4
-    assert L.f3d_workspace_bytes(10, 64, 48) == 256 + 2 * 64 * 48 * 4 and L.f3d_workspace_bytes(10, 0, 8) == 0
+    # ... plus one 112-byte shade record per triangle (up to 2 M triangles)
+    assert L.f3d_workspace_bytes(10, 8192, 8192) == 256 + 2 * 8192 * 8192 * 4 + 10 * 112
+    assert L.f3d_workspace_bytes(3_000_000, 32768, 32768) == 256 + 2 * 8192 * 32768 * 4
+    assert L.f3d_workspace_bytes(0, 64, 48) == 256 + 2 * 64 * 48 * 4 and L.f3d_workspace_bytes(10, 0, 8) == 0
 
 
 def test_argument_validation_without_gpu():

@@ -63,8 +63,7 @@ __device__ __forceinline__ void bary(float px, float py, const Tri& t, float& w0
 
 __device__ __forceinline__ bool accepts(int x, int y, int h, int w, bool inside)
 {
-    const float fx = (float)x, fy = (float)y;
-    return fx < 2.0f || fx > (float)(w - 3) || fy < 2.0f || fy > (float)(h - 3) || inside;
+    return x < 2 || x > w - 3 || y < 2 || y > h - 3 || inside;                // mesh_core.cpp:211 (integer pixel coordinates)
 }
 
 // order-preserving map fp32 -> u32 (NaN never reaches it); +0 and -0 compare equal in the reference's strict '>' test
@@ -177,6 +176,86 @@ __global__ void __launch_bounds__(256) f3d_flat_kernel(const float* __restrict__
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(nonflat, 1);
 }
 
+// Per-triangle record for the shade pass (7 x 16 bytes): origin, edge vectors, dot products, inverse determinant, depths and the
+// three vertex colours -- everything bary_px and the interpolation need, written once per triangle instead of re-derived per
+// pixel from 3 indices + 18 dependent vertex / colour loads and an IEEE division (ncu: 180 instructions per shaded pixel).
+// Same operations in the same order as the per-pixel path, so the bits do not change.  Used when c == 3 and the workspace
+// has room (ntri <= F3D_REC_MAX_TRIS); larger meshes shade from the raw arrays.
+constexpr int F3D_REC_F4 = 7;
+#ifndef F3D_REC_MAX_TRIS
+#define F3D_REC_MAX_TRIS (2 << 20)
+#endif
+
+__global__ void __launch_bounds__(256)
+f3d_setup_kernel(const float* __restrict__ vertices, const int* __restrict__ triangles, const float* __restrict__ colors, int nver, int ntri,
+                 float4* __restrict__ rec)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntri) return;
+    const int i0 = triangles[3 * i], i1 = triangles[3 * i + 1], i2 = triangles[3 * i + 2];
+    float4* __restrict__ r = rec + (size_t)i * F3D_REC_F4;
+    if ((unsigned)i0 >= (unsigned)nver || (unsigned)i1 >= (unsigned)nver || (unsigned)i2 >= (unsigned)nver) return;   // never a winner
+    Tri t;
+    t.x0 = vertices[3 * i0]; t.y0 = vertices[3 * i0 + 1]; t.z0 = vertices[3 * i0 + 2];
+    t.x1 = vertices[3 * i1]; t.y1 = vertices[3 * i1 + 1]; t.z1 = vertices[3 * i1 + 2];
+    t.x2 = vertices[3 * i2]; t.y2 = vertices[3 * i2 + 1]; t.z2 = vertices[3 * i2 + 2];
+    const TriSetup s = tri_setup(t);
+    const float* __restrict__ a0 = colors + 3 * (size_t)i0; const float* __restrict__ a1 = colors + 3 * (size_t)i1;
+    const float* __restrict__ a2 = colors + 3 * (size_t)i2;
+    r[0] = make_float4(t.x0, t.y0, s.v0x, s.v0y);
+    r[1] = make_float4(s.v1x, s.v1y, s.dot00, s.dot01);
+    r[2] = make_float4(s.dot11, s.inv, t.z0, t.z1);
+    r[3] = make_float4(t.z2, a0[0], a0[1], a0[2]);
+    r[4] = make_float4(a1[0], a1[1], a1[2], a2[0]);
+    r[5] = make_float4(a2[1], a2[2], 0.f, 0.f);
+    r[6] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <bool FILL, bool U8>
+__global__ void __launch_bounds__(256)
+f3d_shade_rec_kernel(float* __restrict__ image, uint8_t* __restrict__ image_u8, const float4* __restrict__ rec, float* __restrict__ depth,
+                     float depth_init, int ntri, int h, int w, int y_lo, int y_hi, const unsigned* __restrict__ imax)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    for (int y = y_lo + blockIdx.y; y <= y_hi; y += gridDim.y) {
+        const size_t pix = (size_t)y * w + x;
+        const unsigned key = imax[(size_t)(y - y_lo) * w + x];
+        bool drawn = false;
+        float col[3] = {0.f, 0.f, 0.f};
+        if (key != 0u) {
+            const int idx = (int)(0xffffffffu - key);
+            if (idx >= 0 && idx < ntri) {
+                const float4* __restrict__ r = rec + (size_t)idx * F3D_REC_F4;
+                const float4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2), q3 = __ldg(r + 3), q4 = __ldg(r + 4), q5 = __ldg(r + 5);
+                Tri t;
+                t.x0 = q0.x; t.y0 = q0.y; t.z0 = q2.z; t.z1 = q2.w; t.z2 = q3.x;
+                TriSetup s;
+                s.v0x = q0.z; s.v0y = q0.w; s.v1x = q1.x; s.v1y = q1.y; s.dot00 = q1.z; s.dot01 = q1.w; s.dot11 = q2.x; s.inv = q2.y;
+                float w0, w1, w2; bool inside;
+                bary_px((float)x, (float)y, t, s, w0, w1, w2, inside);
+                const float d = w0 * t.z0 + w1 * t.z1 + w2 * t.z2;
+                drawn = d > (depth ? depth[pix] : depth_init);
+                if (drawn) {
+                    if (depth) depth[pix] = d;
+                    col[0] = w0 * q3.y + w1 * q4.x + w2 * q4.w;
+                    col[1] = w0 * q3.z + w1 * q4.y + w2 * q5.x;
+                    col[2] = w0 * q3.w + w1 * q4.z + w2 * q5.y;
+                }
+            }
+        }
+        if (drawn || FILL) {
+            if (U8) {
+                uint8_t* __restrict__ o = image_u8 + pix * 3;
+                o[0] = (unsigned char)(int)(col[0] * 255.0f); o[1] = (unsigned char)(int)(col[1] * 255.0f); o[2] = (unsigned char)(int)(col[2] * 255.0f);
+            } else {
+                float* __restrict__ o = image + pix * 3;
+                o[0] = col[0]; o[1] = col[1]; o[2] = col[2];
+            }
+        }
+    }
+}
+
 // Pixel-parallel resolve of rows [y_lo, y_hi]: decode the winner, recompute its weights (same bits), depth-test against the
 // caller's depth buffer -- or against the constant `depth_init` when the caller has none (face3d/mesh/render.py:68 creates its
 // own, filled with -999999, and throws it away: 268 MB of reads and 268 MB of writes at 8192^2 for nothing) -- and write.
@@ -281,7 +360,8 @@ static int f3d_band_rows(int ntri, int h, int w)
 extern "C" size_t f3d_workspace_bytes(int32_t ntri, int32_t h, int32_t w)
 {
     if (h < 1 || w < 1) return 0;
-    return 256 + 2 * (size_t)f3d_band_rows(ntri, h, w) * (size_t)w * sizeof(unsigned);
+    const size_t recs = (ntri > 0 && ntri <= F3D_REC_MAX_TRIS) ? (size_t)ntri * F3D_REC_F4 * sizeof(float4) : 0;
+    return 256 + gs_align_up(2 * (size_t)f3d_band_rows(ntri, h, w) * (size_t)w * sizeof(unsigned), 16) + recs;
 }
 
 static int f3d_run(float* image, uint8_t* image_u8, bool fill, const float* vertices, const int32_t* triangles, const float* colors,
@@ -296,10 +376,13 @@ static int f3d_run(float* image, uint8_t* image_u8, bool fill, const float* vert
     int* nonflat = (int*)workspace;
     unsigned* imax = (unsigned*)((char*)workspace + 256);
     unsigned* dmax = imax + (size_t)band * w;
+    float4* rec = (c == 3 && ntri > 0 && ntri <= F3D_REC_MAX_TRIS)
+                      ? (float4*)((char*)workspace + 256 + gs_align_up(2 * (size_t)band * w * sizeof(unsigned), 16)) : nullptr;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaMemsetAsync(nonflat, 0, 256, s) != cudaSuccess) return F3D_E_CUDA;
     if (nver > 0) f3d_flat_kernel<<<sms * 2, 256, 0, s>>>(vertices, nver, nonflat);
+    if (rec) f3d_setup_kernel<<<(ntri + 255) / 256, 256, 0, s>>>(vertices, triangles, colors, nver, ntri, rec);
     const long long warps_needed = ((long long)ntri + 31) / 32;
     long long blocks1 = (warps_needed + 7) / 8;
     if (blocks1 > (long long)sms * 64) blocks1 = (long long)sms * 64;
@@ -313,7 +396,12 @@ static int f3d_run(float* image, uint8_t* image_u8, bool fill, const float* vert
             f3d_tri_kernel<1><<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, y_lo, y_hi, nonflat, dmax, imax);
         }
         const dim3 grid2((unsigned)((w + 255) / 256), (unsigned)(rows < 65535 ? rows : 65535));
-        if (fill && image_u8)
+        if (rec) {
+            if (fill && image_u8) f3d_shade_rec_kernel<true, true><<<grid2, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
+            else if (fill) f3d_shade_rec_kernel<true, false><<<grid2, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
+            else if (image_u8) f3d_shade_rec_kernel<false, true><<<grid2, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
+            else f3d_shade_rec_kernel<false, false><<<grid2, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
+        } else if (fill && image_u8)
             f3d_shade_kernel<true, true><<<grid2, 256, 0, s>>>(image, image_u8, vertices, triangles, colors, depth_buffer, depth_init, nver, ntri, h, w, c, y_lo, y_hi, imax);
         else if (fill)
             f3d_shade_kernel<true, false><<<grid2, 256, 0, s>>>(image, image_u8, vertices, triangles, colors, depth_buffer, depth_init, nver, ntri, h, w, c, y_lo, y_hi, imax);
