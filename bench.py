@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "upstream_style"])
-    ap.add_argument("--workloads", default="all", help="comma list of config2,geometry,texture,bake ('all' = every one at N = 1, "
+    ap.add_argument("--workloads", default="all", help="comma list of config2,geometry,texture,bake,train ('all' = every one at N = 1, "
                     "config2 only at N > 1); the headline metric is always config2, the others are extra keys of the same line")
     ap.add_argument("--views", type=int, default=24)
     ap.add_argument("--width", type=int, default=1920)
@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--opacity", default="topo4d", choices=["topo4d", "generic"])
     ap.add_argument("--views-per-launch", type=int, default=0, help="0 = all local views in one launch sequence")
     ap.add_argument("--cpu-sample-views", type=int, default=24, help="views in the cpu_baseline sample (ours arm)")
-    ap.add_argument("--ref-views-per-step", type=int, default=4, help="views per step of the --impl reference arm")
+    ap.add_argument("--ref-views-per-step", type=int, default=24, help="views per step of the --impl reference arm (24 = the whole "
+                    "workload: ~2 s per step on 16 host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-upstream-style", action="store_true", help="skip the upstream-style CUDA denominator (ours arm, N = 1)")
@@ -64,14 +65,18 @@ def workload(a):
     return scene, cams
 
 
-def config_dict(a, extra=None):
-    d = {"workload": f"BASELINE config 2: {a.views} views {a.width}x{a.height}, {a.gaussians} mesh-bound Gaussians "
-                     f"(head ellipsoid), SH degree {a.sh_degree}, opacity regime '{a.opacity}', depth+alpha consumed",
-         "views": a.views, "width": a.width, "height": a.height, "gaussians": a.gaussians, "sh_degree": a.sh_degree,
-         "l2": "per-step pixel streams (~2.8 GB over 24 views) exceed the 126 MB L2; no explicit flush"}
-    if extra:
-        d.update(extra)
-    return d
+def config_dict(a, world=None):
+    """The workload definition, identical for every arm (--impl ours / reference / upstream_style) at the same N: measured
+    statistics of the scene (instance counts, coverage) are reported under `workload_stats`, notes about an arm under `note`."""
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    per_rank = len(range(0, a.views, world))
+    vpl = a.views_per_launch if a.views_per_launch > 0 else per_rank
+    return {"workload": f"BASELINE config 2: {a.views} views {a.width}x{a.height}, {a.gaussians} mesh-bound Gaussians "
+                        f"(head ellipsoid), SH degree {a.sh_degree}, opacity regime '{a.opacity}', depth+alpha consumed",
+            "views": a.views, "width": a.width, "height": a.height, "gaussians": a.gaussians, "sh_degree": a.sh_degree,
+            "l2": "per-step pixel streams (~2.8 GB over 24 views) exceed the 126 MB L2; no explicit flush",
+            "views_per_rank": per_rank, "views_per_launch": vpl,
+            "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of the flat fp32 gradient buffer per step"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -118,8 +123,8 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(a, {"note": "reference rasterizer is CUDA-only and not vendored; this arm is the CPU "
-                                              "oracle port (oracle/gs_oracle.c, OpenMP over tiles)"}),
+            "config": config_dict(a, a.gpus),
+            "note": "reference rasterizer is CUDA-only and not vendored; this arm is the CPU oracle port (oracle/gs_oracle.c, OpenMP over tiles)",
             "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -231,9 +236,10 @@ def run_upstream_style(a):
     value = a.views * H * W / 1e6 / (ms / 1e3)
     line = {"impl": "upstream_style", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 1),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(a, {"num_rendered": rendered, "note": "upstream-style CUDA pipeline (tools/upstream_style/us_raster.cu): CUB scan + "
-                                      "host read of num_rendered, duplicateWithKeys, 64-bit CUB radix sort, 16x16 block per tile, per-thread global "
-                                      "atomics in the backward; preprocess forward/backward are this repository's kernels; one view per call"})}
+            "config": config_dict(a, 1), "workload_stats": {"num_rendered": rendered},
+            "note": "upstream-style CUDA pipeline (tools/upstream_style/us_raster.cu): CUB scan + host read of num_rendered, duplicateWithKeys, "
+                    "64-bit CUB radix sort, 16x16 block per tile, per-thread global atomics in the backward; preprocess forward/backward are "
+                    "this repository's kernels; one view per call"}
     print(json.dumps(line), flush=True)
 
 
@@ -579,15 +585,14 @@ def run_ours(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": config_dict(a, {"views_per_rank": len(my_views), "views_per_launch": vpl,
-                                          "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of the flat fp32 gradient buffer per step",
-                                          "num_rendered_rank0": stats["num_rendered"], "max_tile_instances": stats["max_tile"],
-                                          "non_empty_tiles_rank0": stats["active_tiles"],
-                                          "mean_tile_instances": (stats["num_rendered"] / stats["active_tiles"]) if stats["active_tiles"] else None,
-                                          "covered_pixel_fraction_rank0": (stats["covered_pixels"] / (len(my_views) * H * W))
-                                          if stats["covered_pixels"] is not None else None,
-                                          "mean_n_contrib_covered_pixels": (stats["n_contrib_sum"] / stats["covered_pixels"])
-                                          if stats["covered_pixels"] else None}),
+                "config": config_dict(a, world),
+                "workload_stats": {"num_rendered_rank0": stats["num_rendered"], "max_tile_instances": stats["max_tile"],
+                                   "non_empty_tiles_rank0": stats["active_tiles"],
+                                   "mean_tile_instances": (stats["num_rendered"] / stats["active_tiles"]) if stats["active_tiles"] else None,
+                                   "covered_pixel_fraction_rank0": (stats["covered_pixels"] / (len(my_views) * H * W))
+                                   if stats["covered_pixels"] is not None else None,
+                                   "mean_n_contrib_covered_pixels": (stats["n_contrib_sum"] / stats["covered_pixels"])
+                                   if stats["covered_pixels"] else None},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof}
         if verify is not None:
             line["verify"] = verify
@@ -617,7 +622,7 @@ def run_ours(a):
             except Exception as e:  # noqa: BLE001
                 line["upstream_style"] = {"error": repr(e)[:300]}
         # the reference's own regimes and config 4, as extra keys of the same line (N = 1 only)
-        wl = [w for w in ("geometry", "texture", "bake") if a.workloads == "all" or w in a.workloads.split(",")]
+        wl = [w for w in ("geometry", "texture", "bake", "train") if a.workloads == "all" or w in a.workloads.split(",")]
         if world == 1 and wl:
             del t, gimgs, flat_bufs
             torch.cuda.empty_cache()

@@ -4,6 +4,8 @@
             ONE view per optimiser step (train.py:105-112,661-673), colors_precomp, opacity 1: eager and CUDA-graph replay
   texture   4 M UV-densified Gaussians at 4096 x 3000 (helpers.py:608-609, train.py:596,715-743), one view per step
   bake      face3d render_colors at 8192^2, 120 050 and 9.59 M triangles (config 4; helpers.py:953-960)
+  train     a short run of the config-5 stand-in (tools/train_synthetic.py: the reference-shaped per-frame loop on a synthetic
+            24-view sequence read from JPEG files through the frame prefetcher, fused loss / Adam, per-frame bake)
 
 Each returns a plain dict that bench.py attaches under "workloads" on its one JSON line.  Device-timed with CUDA events
 after warm-up; inputs resident unless a key says otherwise.  Nothing here imports oracle/ except the bake's CPU column
@@ -214,3 +216,24 @@ def bake(grids=(245, 2190), res: int = 8192, iters: int = 5, cpu: bool = True, d
     return {"what": f"BASELINE config 4: face3d render_colors at {res}x{res}, c = 3 (gpu_ms: the bake as render.py performs it, inputs "
                     "resident, kernels only; gpu_ms_inplace_api: the in-place image + depth contract of render_colors_core; e2e_*: through "
                     "the NumPy-facing drop-in with host arrays, steady state)", "peak_source": src, **out}
+
+
+def train(frames: int = 4, iters: int = 100) -> dict:
+    """BASELINE config 5 in miniature (the 100-frame, 8-GPU run is profiles/r02k_config5_g8.json): one process, a few frames."""
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "train.json")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "train_synthetic.py"), "--frames", str(frames), "--iters", str(iters),
+                            "--files", os.path.join(d, "seq"), "--bake", "1024", "--json", out], capture_output=True, text=True, cwd=ROOT,
+                           timeout=600)
+        if r.returncode != 0:
+            return {"error": r.stderr[-400:]}
+        rep = json.load(open(out))
+    fr = rep["frames"]
+    return {"what": f"config-5 stand-in, {frames} frames x {iters} one-view optimiser steps, 8280 Gaussians, 512x375, 24 cameras, ground truth from "
+                    "JPEG files via FramePrefetcher, image loss + FusedAdam + per-frame 1024^2 bake (tools/train_synthetic.py)",
+            "steps_per_s": rep["steps_per_s"], "ms_per_step_last_frame": fr[-1]["ms_per_step"], "psnr_db_last_frame": fr[-1]["psnr_db"],
+            "mean_vertex_err_m_last_frame": fr[-1]["mean_vertex_err_m"], "bake_ms_last_frame": fr[-1].get("bake_ms"),
+            "loss_first": fr[0]["loss_first"], "loss_last": fr[-1]["loss_last"]}
