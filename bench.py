@@ -76,7 +76,7 @@ def config_dict(a, world=None):
             "views": a.views, "width": a.width, "height": a.height, "gaussians": a.gaussians, "sh_degree": a.sh_degree,
             "l2": "per-step pixel streams (~2.8 GB over 24 views) exceed the 126 MB L2; no explicit flush",
             "views_per_rank": per_rank, "views_per_launch": vpl,
-            "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of the flat fp32 gradient buffer per step"}
+            "parallelism": f"view-parallel x{world}, 1 all-reduce of the flat fp32 gradient buffer per step"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -244,6 +244,7 @@ def run_upstream_style(a):
 
 
 def measure_e2e(a, dev, world, rank, host, cam_groups, gimgs, H, W, use_sh, n_grad):
+    from topo4d_b200 import parallel
     """End-to-end steps through the plugin.  Per step: ONE host->device copy of the packed parameters (rank 0; the other ranks
     receive them by an NCCL broadcast over NVLink instead of each pulling 14 MB through its own PCIe link), render_views +
     autograd backward of the local views, gradients reduced to rank 0 (one NCCL reduce) and ONE device->host copy of the flat
@@ -265,7 +266,8 @@ def measure_e2e(a, dev, world, rank, host, cam_groups, gimgs, H, W, use_sh, n_gr
         s0, n, _ = offs[k]
         host_in[s0:s0 + n].copy_(host[k].reshape(-1))
     dev_in = [torch.empty(n_in, dtype=torch.float32, device=dev) for _ in range(2)]
-    dev_out = [torch.empty(n_grad, dtype=torch.float32, device=dev) for _ in range(2)]
+    dev_out = [parallel.symmetric_flat(n_grad, dev) for _ in range(2)]          # exchangeable in-switch from 8 ranks up
+    dev_out = [b if b is not None else torch.empty(n_grad, dtype=torch.float32, device=dev) for b in dev_out]
     host_out = [torch.empty(n_grad, dtype=torch.float32).pin_memory() for _ in range(2)]
     part = [torch.empty(n_grad, dtype=torch.float32, device=dev) for _ in range(len(cam_groups) - 1)]
     main = torch.cuda.current_stream(dev)
@@ -314,7 +316,10 @@ def measure_e2e(a, dev, world, rank, host, cam_groups, gimgs, H, W, use_sh, n_gr
         with torch.cuda.stream(stream):
             stream.wait_event(ev_done[b])
             if world > 1:
-                dist.reduce(dev_out[b], dst=0)
+                if dev_out[b].data_ptr() in parallel._SYMM:
+                    parallel.allreduce_flat_(dev_out[b])            # in-switch all-reduce (as cheap as a reduce to one rank)
+                else:
+                    dist.reduce(dev_out[b], dst=0)
             if rank == 0:
                 host_out[b].copy_(dev_out[b], non_blocking=True)
             ev_out[b].record(stream)
@@ -442,6 +447,9 @@ def run_ours(a):
         del color, depth, alpha, st, target
     flat = None
     flat_bufs = [None] * len(groups)      # gradient buffers are allocated once and reused (the all-reduce runs in place)
+    n_flat = engine.flat_layout(a.gaussians, int(t["shs"].shape[1]) if use_sh else 0, use_sh, False)[1]
+    flat_bufs[0] = parallel.symmetric_flat(n_flat, dev)          # NVLink symmetric memory from 8 ranks up (None: plain tensor + NCCL)
+    exchange = "symmetric-memory multimem all-reduce (NVSwitch in-switch reduction)" if flat_bufs[0] is not None else "ncclAllReduce"
 
     def step(params, ev=None):
         nonlocal flat
@@ -594,6 +602,8 @@ def run_ours(a):
                                    "mean_n_contrib_covered_pixels": (stats["n_contrib_sum"] / stats["covered_pixels"])
                                    if stats["covered_pixels"] else None},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof}
+        if world > 1:
+            line["exchange"] = exchange
         if verify is not None:
             line["verify"] = verify
         # pairs / covered-pixel rates beside the headline (94.6 % of this workload's pixels are background fill)
