@@ -805,32 +805,24 @@ blend_bwd_mma_kernel(const GsParams p, const GsBackwardIO io)
             // dy = ey - y'), then gradients of the 2-D record (pix.x, pix.y, conic A, B | C, opacity, depth, _ | rgb), conic B being
             // the true (not halved) derivative; one 16-byte RED per (record, part).
             __syncwarp();
-            for (int u = lane; u < nt * 3; u += 32) {
-                const int r = u / 3, part = u - r * 3;
-                const float4 m1 = my_acc[r * 3 + 1];
+            // one lane per reduced record (nt <= 32 rows): three 16-byte row reads (48-byte stride: conflict-free), the record, three REDs --
+            // ONE pass per chunk (the (record, part) -> lane mapping took 1.6 passes of the same length)
+            if (lane < nt) {
+                const float4 m0 = my_acc[lane * 3], m1 = my_acc[lane * 3 + 1], mw = my_acc[lane * 3 + 2];
                 const int j = __float_as_int(m1.y);
                 const float4 q0 = rec[j * 3], q1 = rec[j * 3 + 1];
-                const float o = q1.y;
-                float4 a;
-                if (part == 2) {
-                    const float4 mw = my_acc[r * 3 + 2];
-                    a = make_float4(mw.z, mw.y, mw.w, 0.f);
-                } else {
-                    const float4 m0 = my_acc[r * 3];
-                    const float ex = __fsub_rn(q0.x, fxc0), ey = __fsub_rn(q0.y, fyc0);
-                    const float M1 = m0.x, My = m0.y, Mx = m0.z, Mxy = m0.w, Myy = m1.x, Mxx = m1.z;
-                    const float Sx = __fmaf_rn(ex, M1, -Mx), Sy = __fmaf_rn(ey, M1, -My);      // sum tt dx, sum tt dy
-                    if (part == 0) {
-                        const float Sxx = __fmaf_rn(ex, Sx - Mx, Mxx);                          // ex^2 M1 - 2 ex Mx + Mxx
-                        const float Sxy = __fmaf_rn(ex, Sy, __fmaf_rn(-ey, Mx, Mxy));            // ex ey M1 - ex My - ey Mx + Mxy
-                        a = make_float4(-o * (q0.z * Sx + q0.w * Sy), -o * (q1.x * Sy + q0.w * Sx), -0.5f * o * Sxx, -o * Sxy);
-                    } else {
-                        const float Syy = __fmaf_rn(ey, Sy - My, Myy);
-                        a = make_float4(-0.5f * o * Syy, M1, my_acc[r * 3 + 2].x, 0.f);
-                    }
-                }
                 const int id = __float_as_int(rec[j * 3 + 2].w) & 0x00ffffff;
-                red_add_v4(gbase + (size_t)id * 3 + part, a);
+                const float o = q1.y;
+                const float ex = __fsub_rn(q0.x, fxc0), ey = __fsub_rn(q0.y, fyc0);
+                const float M1 = m0.x, My = m0.y, Mx = m0.z, Mxy = m0.w, Myy = m1.x, Mxx = m1.z;
+                const float Sx = __fmaf_rn(ex, M1, -Mx), Sy = __fmaf_rn(ey, M1, -My);      // sum tt dx, sum tt dy
+                const float Sxx = __fmaf_rn(ex, Sx - Mx, Mxx);                              // ex^2 M1 - 2 ex Mx + Mxx
+                const float Sxy = __fmaf_rn(ex, Sy, __fmaf_rn(-ey, Mx, Mxy));                // ex ey M1 - ex My - ey Mx + Mxy
+                const float Syy = __fmaf_rn(ey, Sy - My, Myy);
+                float4* __restrict__ dst = gbase + (size_t)id * 3;
+                red_add_v4(dst, make_float4(-o * (q0.z * Sx + q0.w * Sy), -o * (q1.x * Sy + q0.w * Sx), -0.5f * o * Sxx, -o * Sxy));
+                red_add_v4(dst + 1, make_float4(-0.5f * o * Syy, M1, mw.x, 0.f));
+                red_add_v4(dst + 2, make_float4(mw.z, mw.y, mw.w, 0.f));
             }
         }
         __syncwarp();
