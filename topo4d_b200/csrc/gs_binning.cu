@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 8) sort_gather_kernel(const GsPa
         if (end > (unsigned long long)p.cap) end = (unsigned long long)p.cap;
         if (start >= end) continue;
         const int n = (int)(end - start);
-        const int v = (int)(tg / p.tiles);
+        const int v = (int)((unsigned)tg / (unsigned)p.tiles);             // V * tiles < 2^31 (validated on the host)
         unsigned long long* gk = p.pairs + start;
         unsigned long long* sorted = s_keys;
         if (n <= 128 * 2) sort_tile_regs<2>(gk, n, tid, s_keys);
@@ -395,7 +395,13 @@ __global__ void __launch_bounds__(SORT_THREADS, 8) sort_gather_kernel(const GsPa
             const int k = t / 3, part = t - k * 3;
             const uint32_t low = (uint32_t)sorted[k];
             float4 val = __ldg(geom + (size_t)(low & 0x00ffffffu) * 3 + part);
-            if (part == 2) val.w = __uint_as_float(low);           // id | reach mask << 24
+#if GS_PRESCALE
+            if (part == 0) { val.z *= -0.5f; val.w = -val.w; }     // conic pre-scaled for the blend kernels: -A/2, -B (exact)
+            else if (part == 1) val.x *= -0.5f;                    // -C/2
+            else val.w = __uint_as_float(low);                     // id | reach mask << 24
+#else
+            if (part == 2) val.w = __uint_as_float(low);
+#endif
             rec[t] = val;
         }
         __syncthreads();   // s_keys is reused by the next tile
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(SORT_LONG_THREADS, 1) sort_gather_long_kernel(
                 }
                 __syncthreads();
             }
-        const int v = (int)(tg / p.tiles);
+        const int v = (int)((unsigned)tg / (unsigned)p.tiles);             // V * tiles < 2^31 (validated on the host)
         const float4* __restrict__ geom = p.geom + (size_t)v * p.N * 3;
         float4* __restrict__ rec = p.sorted_rec + start * 3;
         const int tl = (int)(tg - (long long)v * p.tiles);
@@ -456,7 +462,13 @@ __global__ void __launch_bounds__(SORT_LONG_THREADS, 1) sort_gather_long_kernel(
             const int k = t / 3, part = t - k * 3;
             const uint32_t low = (uint32_t)s_long[k];
             float4 val = __ldg(geom + (size_t)(low & 0x00ffffffu) * 3 + part);
-            if (part == 2) val.w = __uint_as_float(low);           // id | reach mask << 24
+#if GS_PRESCALE
+            if (part == 0) { val.z *= -0.5f; val.w = -val.w; }     // conic pre-scaled for the blend kernels: -A/2, -B (exact)
+            else if (part == 1) val.x *= -0.5f;                    // -C/2
+            else val.w = __uint_as_float(low);                     // id | reach mask << 24
+#else
+            if (part == 2) val.w = __uint_as_float(low);
+#endif
             rec[t] = val;
         }
         __syncthreads();

@@ -73,12 +73,20 @@ constexpr uint32_t REC_BYTES = 48;
 
 // ---- per-pair arithmetic shared by forward and backward (identical bits in both) ----
 struct ColTerms { float hC, u, v; };          // power(dy) = dy*(hC*dy + u) + v for a fixed pixel column
-__device__ __forceinline__ ColTerms col_terms(float cA, float cB, float cC, float dx)
+// The tile-sorted records carry the conic PRE-SCALED (hA = -A/2, nB = -B, hC = -C/2; gs_binning.cu writes them that way): scaling by a
+// power of two and negation commute with rounding, so these three products have the bits of -0.5*(A*dx)*dx, -(B*dx), -0.5*C.
+__device__ __forceinline__ ColTerms col_terms(float hA, float nB, float hC, float dx)
 {
     ColTerms r;
-    r.hC = __fmul_rn(-0.5f, cC);
-    r.u = -__fmul_rn(cB, dx);
-    r.v = __fmul_rn(__fmul_rn(-0.5f, __fmul_rn(cA, dx)), dx);
+#if GS_PRESCALE
+    r.hC = hC;
+    r.u = __fmul_rn(nB, dx);
+    r.v = __fmul_rn(__fmul_rn(hA, dx), dx);
+#else
+    r.hC = __fmul_rn(-0.5f, hC);
+    r.u = -__fmul_rn(nB, dx);
+    r.v = __fmul_rn(__fmul_rn(-0.5f, __fmul_rn(hA, dx)), dx);
+#endif
     return r;
 }
 __device__ __forceinline__ float splat_power(const ColTerms& r, float dy)
@@ -99,6 +107,14 @@ __device__ __forceinline__ float splat_exp(float power)
     float y = __fmul_rn(power, LOG2E), g;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(y));
     return g;
+#elif GS_EXP_MODE == 3
+    // mode 2 without the log2(e) tail term: |power| <= 5.6 on the blend path, so dropping power * 1.9e-8 costs <= 1.1e-7 relative (one more ulp)
+    const float L2E_HI = 1.4426950216293335f, LN2 = 0.6931471805599453f;
+    const float y = __fmul_rn(power, L2E_HI);
+    const float r = __fmaf_rn(power, L2E_HI, -y);
+    float g;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(y));
+    return __fmaf_rn(g, __fmul_rn(r, LN2), g);
 #else
     const float L2E_HI = 1.4426950216293335f, L2E_LO = 1.9259629911266175e-8f, LN2 = 0.6931471805599453f;
     const float y = __fmul_rn(power, L2E_HI);
@@ -571,7 +587,12 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
                 float4 a = my_acc[t];
                 const float4 q0 = rec[j * 3], q1 = rec[j * 3 + 1];
                 const float o = q1.y;
+                // q0.z, q0.w, q1.x = -A/2, -B, -C/2 (pre-scaled conic)
+#if GS_PRESCALE
+                if (part == 0) a = make_float4(o * __fmaf_rn(2.0f * q0.z, a.x, q0.w * a.y), o * __fmaf_rn(2.0f * q1.x, a.y, q0.w * a.x), -0.5f * o * a.z, -o * a.w);
+#else
                 if (part == 0) a = make_float4(-o * (q0.z * a.x + q0.w * a.y), -o * (q1.x * a.y + q0.w * a.x), -0.5f * o * a.z, -o * a.w);
+#endif
                 else if (part == 1) a.x = -0.5f * o * a.x;
                 const int id = __float_as_int(rec[j * 3 + 2].w) & 0x00ffffff;
                 red_add_v4(gbase + (size_t)id * 3 + part, a);
@@ -820,7 +841,12 @@ blend_bwd_mma_kernel(const GsParams p, const GsBackwardIO io)
                 const float Sxy = __fmaf_rn(ex, Sy, __fmaf_rn(-ey, Mx, Mxy));                // ex ey M1 - ex My - ey Mx + Mxy
                 const float Syy = __fmaf_rn(ey, Sy - My, Myy);
                 float4* __restrict__ dst = gbase + (size_t)id * 3;
+                // q0.z, q0.w, q1.x = -A/2, -B, -C/2 (pre-scaled conic): dL/dpix = -o (A Sx + B Sy), -o (C Sy + B Sx)
+#if GS_PRESCALE
+                red_add_v4(dst, make_float4(o * __fmaf_rn(2.0f * q0.z, Sx, q0.w * Sy), o * __fmaf_rn(2.0f * q1.x, Sy, q0.w * Sx), -0.5f * o * Sxx, -o * Sxy));
+#else
                 red_add_v4(dst, make_float4(-o * (q0.z * Sx + q0.w * Sy), -o * (q1.x * Sy + q0.w * Sx), -0.5f * o * Sxx, -o * Sxy));
+#endif
                 red_add_v4(dst + 1, make_float4(-0.5f * o * Syy, M1, mw.x, 0.f));
                 red_add_v4(dst + 2, make_float4(mw.z, mw.y, mw.w, 0.f));
             }

@@ -13,7 +13,8 @@
 //                                                   thr = conservative lower bound of `power` for alpha >= 1/255
 //   pairs         u64 [cap]                         (depth_bits<<32 | id), tile-major, unsorted
 //   sorted_ids    u32 [cap]
-//   sorted_rec    48-byte record [cap]              tile-sorted copy of geom: ONE contiguous bulk copy per chunk
+//   sorted_rec    48-byte record [cap]              tile-sorted copy of geom: ONE contiguous bulk copy per chunk; conic pre-scaled
+//                                                   (x,y,-conA/2,-conB | -conC/2,opacity,depth,thr | r,g,b,id + reach mask << 24)
 //   final_T       f32 [V*H*W]
 //   n_contrib     u32 [V*H*W]
 //   grad2d        48-byte record [V*N]              (dpix.x,dpix.y,dconA,dconB | dconC,dopacity,ddepth,_ | dr,dg,db,_)
@@ -24,6 +25,9 @@
 #include "../../include/topo4d_b200.h"
 
 #define GS_TILE 16
+#ifndef GS_PRESCALE
+#define GS_PRESCALE 1
+#endif
 #define GS_REC_FLOATS 12            // 48-byte records
 #define GS_NEAR_CULL 0.2f
 #define GS_LOWPASS 0.3f

@@ -49,17 +49,19 @@ __global__ void __launch_bounds__(128, 4) preprocess_kernel(const GsParams p, in
 {
     __shared__ float s_cam[2][GS_CAM_FLOATS];
     __shared__ __align__(16) float s_sh[4][32 * SH_ROW];
-    const long long gid0 = (long long)blockIdx.x * blockDim.x;
-    const int v_first = (int)(gid0 / p.N);
+    // (view, Gaussian) index arithmetic in 32 bits: V * N < 2^31 is validated on the host, and a 64-bit division costs ~100 instructions
+    const unsigned Nu = (unsigned)p.N, total = (unsigned)p.V * Nu;
+    const unsigned gid0 = blockIdx.x * blockDim.x;
+    const int v_first = (int)(gid0 / Nu);
     for (int k = threadIdx.x; k < 2 * GS_CAM_FLOATS; k += blockDim.x) {
         const int vv = v_first + k / GS_CAM_FLOATS;
         s_cam[k / GS_CAM_FLOATS][k % GS_CAM_FLOATS] = vv < p.V ? p.cams[(size_t)vv * GS_CAM_FLOATS + k % GS_CAM_FLOATS] : 0.f;
     }
     __syncthreads();
-    const long long gid_raw = gid0 + threadIdx.x;
-    const bool in_range = gid_raw < (long long)p.V * p.N;                        // out-of-range threads still help stage the SH rows
-    const long long gid = in_range ? gid_raw : 0;
-    const int v = (int)(gid / p.N), i = (int)(gid % p.N);
+    const unsigned gid_raw = gid0 + threadIdx.x;
+    const bool in_range = gid_raw < total;                                       // out-of-range threads still help stage the SH rows
+    const unsigned gid = in_range ? gid_raw : 0u;
+    const int v = (int)(gid / Nu), i = (int)(gid - (unsigned)v * Nu);
     const float* __restrict__ cam = s_cam[v - v_first];       // a 128-thread CTA spans at most two views (N >= 128) ...
     if (v - v_first > 1) cam = p.cams + (size_t)v * GS_CAM_FLOATS;   // ... or reads global memory for the rest (tiny N)
     const float* V = cam + GS_CAM_VIEW;
@@ -87,8 +89,8 @@ __global__ void __launch_bounds__(128, 4) preprocess_kernel(const GsParams p, in
     if (sh_fast) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int nf4 = ((p.deg + 1) * (p.deg + 1) * 3 + 3) / 4;                  // 16-byte chunks of a row that are needed
-        const long long g0 = gid0 + warp * 32;                                   // first (view, Gaussian) of this warp
-        const int i0 = (int)(g0 % p.N);
+        const unsigned g0 = gid0 + warp * 32;                                    // first (view, Gaussian) of this warp
+        const int i0 = (int)(g0 % Nu);
         int r = lane / 12, q = lane - r * 12;                                    // chunk c = 32 k + lane = row r, 16-byte column q
         const bool wraps = i0 + 32 > p.N;                                         // the warp straddles a view boundary (or N < 32)
         #pragma unroll
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(128, 4) preprocess_kernel(const GsParams p, in
 
     radii[gid] = (int)radius;
     p.clamped[gid] = (uint8_t)clampbits;
-    float4* g = p.geom + gid * 3;
+    float4* g = p.geom + (size_t)gid * 3;
     g[0] = make_float4(pix_x, pix_y, cA, cB);
     // thr: the blend kernels skip a pixel without evaluating exp() when power < thr.  alpha >= 1/255 needs
     // power >= -ln(255*opacity); the 1e-3 margin (0.1 % in alpha) dwarfs any fp32 rounding of power or exp,
@@ -250,12 +252,12 @@ __global__ void __launch_bounds__(128, 4) preprocess_kernel(const GsParams p, in
 // (atomic cursor); the per-tile sort restores (depth, id) order, a total order on distinct keys.
 __global__ void __launch_bounds__(256) scatter_kernel(const GsParams p, const int32_t* __restrict__ radii)
 {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)p.V * p.N) return;
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;                  // V * N < 2^31 (validated on the host)
+    if (gid >= (unsigned)p.V * (unsigned)p.N) return;
     const int rad = radii[gid];
     if (rad <= 0) return;
-    const int v = (int)(gid / p.N), i = (int)(gid % p.N);
-    const float4 g0 = p.geom[gid * 3], g1 = p.geom[gid * 3 + 1];
+    const int v = (int)(gid / (unsigned)p.N), i = (int)(gid - (unsigned)v * (unsigned)p.N);
+    const float4 g0 = p.geom[(size_t)gid * 3], g1 = p.geom[(size_t)gid * 3 + 1];
     const Rect rc = tile_rect(g0.x, g0.y, (float)rad, p.tiles_x, p.tiles_y);
     const unsigned long long pair = ((unsigned long long)__float_as_uint(g1.z) << 32) | (unsigned)i;
     const size_t tbase = (size_t)v * p.tiles;
