@@ -115,6 +115,24 @@ __device__ __forceinline__ void test_pixel(const Tri& t, const TriSetup& ts, int
 
 constexpr int SMALL_BOX = 48;   // bbox pixels a single lane walks by itself
 
+// The texture bake's case -- every vertex z is 0 and the bbox keeps clear of the 2-pixel image border -- needs no depth and no border
+// rule: a pixel accepts the triangle iff it is inside (then u, v are finite, the interpolated depth is +-0, never NaN), and the winner is
+// the lowest index.  inside_px is bary_px's inside test with the products that depend on one coordinate only passed in: (v0x v2x),
+// (v1x v2x) are computed once per column by the callers, so a pixel costs 17 fp32 operations instead of ~50 instructions of the general
+// test_pixel.  Same operations on the same operands in the same order as the reference (mesh_core.cpp:23-50): same bits.
+__device__ __forceinline__ bool inside_px(const TriSetup& s, float ax, float bx, float v2y)
+{
+    const float dot02 = ax + s.v0y * v2y;
+    const float dot12 = bx + s.v1y * v2y;
+    const float u = (s.dot11 * dot02 - s.dot01 * dot12) * s.inv;
+    const float v = (s.dot00 * dot12 - s.dot01 * dot02) * s.inv;
+    return (u >= 0.0f) && (v >= 0.0f) && (u + v < 1.0f);
+}
+__device__ __forceinline__ bool clear_of_border(int xmin, int xmax, int ymin, int ymax, int h, int w)
+{
+    return xmin >= 2 && xmax <= w - 3 && ymin >= 2 && ymax <= h - 3;
+}
+
 template <int STAGE>
 __global__ void __launch_bounds__(256)
 f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ triangles, int nver, int ntri, int h, int w,
@@ -132,12 +150,23 @@ f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ trian
         if (i < ntri) ok = load_tri(vertices, triangles, i, nver, h, w, y_lo, y_hi, t);
         int bw = 0, area = 0;
         if (ok) { bw = t.xmax - t.xmin + 1; const long long a = (long long)bw * (t.ymax - t.ymin + 1); area = a > 0x7fffffffLL ? 0x7fffffff : (int)a; }
+        const bool fast = STAGE == 1 && flat && ok && clear_of_border(t.xmin, t.xmax, t.ymin, t.ymax, h, w);
         if (ok && area <= SMALL_BOX) {
             const TriSetup ts = tri_setup(t);
-            for (int y = t.ymin; y <= t.ymax; y++)
-                for (int x = t.xmin; x <= t.xmax; x++) test_pixel<STAGE>(t, ts, i, x, y, h, w, y_lo, flat, dmax, imax);
+            if (fast) {
+                for (int x = t.xmin; x <= t.xmax; x++) {
+                    const float v2x = (float)x - t.x0;
+                    const float ax = ts.v0x * v2x, bx = ts.v1x * v2x;
+                    for (int y = t.ymin; y <= t.ymax; y++)
+                        if (inside_px(ts, ax, bx, (float)y - t.y0)) atomicMax(imax + (size_t)(y - y_lo) * w + x, 0xffffffffu - (unsigned)i);
+                }
+            } else {
+                for (int y = t.ymin; y <= t.ymax; y++)
+                    for (int x = t.xmin; x <= t.xmax; x++) test_pixel<STAGE>(t, ts, i, x, y, h, w, y_lo, flat, dmax, imax);
+            }
         }
         unsigned big = __ballot_sync(0xffffffffu, ok && area > SMALL_BOX);
+        const unsigned big_fast = __ballot_sync(0xffffffffu, fast);
         while (big) {
             const int src = __ffs(big) - 1;
             big &= big - 1;
@@ -150,6 +179,23 @@ f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ trian
             const int sarea = __shfl_sync(0xffffffffu, area, src);
             const int sidx = (int)base + src;
             const TriSetup ts = tri_setup(s);                  // once per triangle (every lane computes the same values)
+            if (STAGE == 1 && ((big_fast >> src) & 1u)) {
+                // the warp covers the box in steps of (32 / cw) rows x cw columns, cw = the box width rounded up to a power of two (<= 32):
+                // a lane keeps its column -- the column products are computed once per 32-column block -- and walks down the rows
+                const int sh = sbw > 16 ? 5 : sbw > 8 ? 4 : sbw > 4 ? 3 : sbw > 2 ? 2 : 1;
+                const int col = lane & ((1 << sh) - 1), rof = lane >> sh, rstep = 32 >> sh;
+                const int symax = s.ymin + sarea / sbw - 1;
+                const unsigned key = 0xffffffffu - (unsigned)sidx;
+                for (int x0 = col; x0 < sbw; x0 += 32) {
+                    const int x = s.xmin + x0;
+                    const float v2x = (float)x - s.x0;
+                    const float ax = ts.v0x * v2x, bx = ts.v1x * v2x;
+                    unsigned* __restrict__ dst = imax + (size_t)(s.ymin + rof - y_lo) * w + x;
+                    for (int y = s.ymin + rof; y <= symax; y += rstep, dst += (size_t)rstep * w)
+                        if (inside_px(ts, ax, bx, (float)y - s.y0)) atomicMax(dst, key);
+                }
+                continue;
+            }
             // lanes walk the box in row-major order, 32 pixels per step; (xx, yy) advance incrementally (no division)
             int xx = lane, yy = 0;
             while (xx >= sbw) { xx -= sbw; yy++; }
@@ -251,6 +297,83 @@ f3d_shade_rec_kernel(float* __restrict__ image, uint8_t* __restrict__ image_u8, 
             } else {
                 float* __restrict__ o = image + pix * 3;
                 o[0] = col[0]; o[1] = col[1]; o[2] = col[2];
+            }
+        }
+    }
+}
+
+// The same resolve with FOUR consecutive pixels of a row per thread (w % 4 == 0, 16-byte aligned planes): one 16-byte key load, the
+// triangle record is fetched once per run of equal winners (inside a triangle all four pixels share it), and the twelve colour values
+// leave as three 16-byte stores (fp32) or three 4-byte stores (uint8) instead of twelve scalar ones.  Same per-pixel arithmetic.
+template <bool FILL, bool U8>
+__global__ void __launch_bounds__(256)
+f3d_shade_rec4_kernel(float* __restrict__ image, uint8_t* __restrict__ image_u8, const float4* __restrict__ rec, float* __restrict__ depth,
+                      float depth_init, int ntri, int h, int w, int y_lo, int y_hi, const unsigned* __restrict__ imax)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x4 >= w) return;
+    for (int y = y_lo + blockIdx.y; y <= y_hi; y += gridDim.y) {
+        const size_t pix = (size_t)y * w + x4;
+        const uint4 k4 = *reinterpret_cast<const uint4*>(imax + (size_t)(y - y_lo) * w + x4);
+        const unsigned key[4] = {k4.x, k4.y, k4.z, k4.w};
+        float col[12];
+        bool drawn[4];
+        int cached = -1;
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0, q4 = q0, q5 = q0;
+        #pragma unroll
+        for (int e = 0; e < 4; e++) {
+            drawn[e] = false;
+            col[3 * e] = col[3 * e + 1] = col[3 * e + 2] = 0.f;
+            if (key[e] == 0u) continue;
+            const int idx = (int)(0xffffffffu - key[e]);
+            if (idx < 0 || idx >= ntri) continue;
+            if (idx != cached) {
+                const float4* __restrict__ r = rec + (size_t)idx * F3D_REC_F4;
+                q0 = __ldg(r); q1 = __ldg(r + 1); q2 = __ldg(r + 2); q3 = __ldg(r + 3); q4 = __ldg(r + 4); q5 = __ldg(r + 5);
+                cached = idx;
+            }
+            Tri t;
+            t.x0 = q0.x; t.y0 = q0.y; t.z0 = q2.z; t.z1 = q2.w; t.z2 = q3.x;
+            TriSetup s;
+            s.v0x = q0.z; s.v0y = q0.w; s.v1x = q1.x; s.v1y = q1.y; s.dot00 = q1.z; s.dot01 = q1.w; s.dot11 = q2.x; s.inv = q2.y;
+            float w0, w1, w2; bool inside;
+            bary_px((float)(x4 + e), (float)y, t, s, w0, w1, w2, inside);
+            const float d = w0 * t.z0 + w1 * t.z1 + w2 * t.z2;
+            drawn[e] = d > (depth ? depth[pix + e] : depth_init);
+            if (drawn[e]) {
+                if (depth) depth[pix + e] = d;
+                col[3 * e] = w0 * q3.y + w1 * q4.x + w2 * q4.w;
+                col[3 * e + 1] = w0 * q3.z + w1 * q4.y + w2 * q5.x;
+                col[3 * e + 2] = w0 * q3.w + w1 * q4.z + w2 * q5.y;
+            }
+        }
+        if (FILL || (drawn[0] && drawn[1] && drawn[2] && drawn[3])) {
+            if (U8) {
+                unsigned b[3];
+                #pragma unroll
+                for (int q = 0; q < 3; q++)
+                    b[q] = (unsigned)(unsigned char)(int)(col[4 * q] * 255.0f) | ((unsigned)(unsigned char)(int)(col[4 * q + 1] * 255.0f) << 8) |
+                           ((unsigned)(unsigned char)(int)(col[4 * q + 2] * 255.0f) << 16) | ((unsigned)(unsigned char)(int)(col[4 * q + 3] * 255.0f) << 24);
+                unsigned* __restrict__ o = reinterpret_cast<unsigned*>(image_u8 + pix * 3);
+                o[0] = b[0]; o[1] = b[1]; o[2] = b[2];
+            } else {
+                float4* __restrict__ o = reinterpret_cast<float4*>(image + pix * 3);
+                o[0] = make_float4(col[0], col[1], col[2], col[3]);
+                o[1] = make_float4(col[4], col[5], col[6], col[7]);
+                o[2] = make_float4(col[8], col[9], col[10], col[11]);
+            }
+        } else {
+            #pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (!drawn[e]) continue;
+                if (U8) {
+                    uint8_t* __restrict__ o = image_u8 + (pix + e) * 3;
+                    o[0] = (unsigned char)(int)(col[3 * e] * 255.0f); o[1] = (unsigned char)(int)(col[3 * e + 1] * 255.0f);
+                    o[2] = (unsigned char)(int)(col[3 * e + 2] * 255.0f);
+                } else {
+                    float* __restrict__ o = image + (pix + e) * 3;
+                    o[0] = col[3 * e]; o[1] = col[3 * e + 1]; o[2] = col[3 * e + 2];
+                }
             }
         }
     }
@@ -396,7 +519,14 @@ static int f3d_run(float* image, uint8_t* image_u8, bool fill, const float* vert
             f3d_tri_kernel<1><<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, y_lo, y_hi, nonflat, dmax, imax);
         }
         const dim3 grid2((unsigned)((w + 255) / 256), (unsigned)(rows < 65535 ? rows : 65535));
-        if (rec) {
+        const bool vec4 = rec && (w & 3) == 0 && (((uintptr_t)image | (uintptr_t)image_u8 | (uintptr_t)imax) & 15u) == 0;
+        if (vec4) {
+            const dim3 grid4((unsigned)((w / 4 + 255) / 256), grid2.y);
+            if (fill && image_u8) f3d_shade_rec4_kernel<true, true><<<grid4, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
+            else if (fill) f3d_shade_rec4_kernel<true, false><<<grid4, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
+            else if (image_u8) f3d_shade_rec4_kernel<false, true><<<grid4, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
+            else f3d_shade_rec4_kernel<false, false><<<grid4, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
+        } else if (rec) {
             if (fill && image_u8) f3d_shade_rec_kernel<true, true><<<grid2, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
             else if (fill) f3d_shade_rec_kernel<true, false><<<grid2, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
             else if (image_u8) f3d_shade_rec_kernel<false, true><<<grid2, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);

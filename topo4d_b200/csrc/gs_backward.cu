@@ -13,6 +13,10 @@
 #include "gs_common.cuh"
 
 
+#ifndef GS_PBWD_PREFETCH
+#define GS_PBWD_PREFETCH 1
+#endif
+
 namespace {
 
 __device__ __constant__ float bC0 = 0.28209479177387814f;
@@ -100,6 +104,38 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
     #pragma unroll
     for (int k = 0; k < KK * 3; k++) gsh[k] = 0.f;
 
+#if GS_PBWD_PREFETCH
+    // the per-(view, Gaussian) inputs of the NEXT view of this lane are requested before the arithmetic of the current one (the kernel
+    // waits on these loads: long-scoreboard 3.2 per issue at 12 warps per SM)
+    int v_next = vq;
+    int rad_n = 0;
+    unsigned cl_n = 0u;
+    float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0, n2 = n0;
+    if (act && v_next < p.V) {
+        const size_t g = (size_t)v_next * p.N + i;
+        rad_n = io.radii[g]; n0 = p.grad2d[g * 3]; n1 = p.grad2d[g * 3 + 1]; n2 = p.grad2d[g * 3 + 2];
+        if constexpr (K > 0) cl_n = p.clamped[g];
+    }
+    while (act && v_next < p.V) {
+        const int v = v_next;
+        const int rad = rad_n;
+        const float4 a0 = n0, a1 = n1, a2 = n2;
+        [[maybe_unused]] const unsigned cl = cl_n;
+        v_next += LPG;
+        if (v_next < p.V) {
+            const size_t g = (size_t)v_next * p.N + i;
+            rad_n = io.radii[g]; n0 = p.grad2d[g * 3]; n1 = p.grad2d[g * 3 + 1]; n2 = p.grad2d[g * 3 + 2];
+            if constexpr (K > 0) cl_n = p.clamped[g];
+        }
+        if (rad <= 0) continue;
+        const float* __restrict__ cam = p.cams + (size_t)v * GS_CAM_FLOATS;
+        const float* V = cam + GS_CAM_VIEW;
+        const float* P = cam + GS_CAM_PROJ;
+        const float g_px = a0.x, g_py = a0.y, gA = a0.z, gB = a0.w, gC = a1.x, g_o = a1.y, g_d = a1.z;
+        gop += g_o;
+
+        if constexpr (K > 0) {
+#else
     for (int v = vq; v < p.V && act; v += LPG) {
         const size_t gid = (size_t)v * p.N + i;
         if (io.radii[gid] <= 0) continue;
@@ -112,6 +148,7 @@ preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
 
         if constexpr (K > 0) {
             const unsigned cl = p.clamped[gid];
+#endif
             const float dx = px - cam[GS_CAM_CAMPOS], dy = py - cam[GS_CAM_CAMPOS + 1], dz = pz - cam[GS_CAM_CAMPOS + 2];
             const float inv_len = rsqrtf(dx * dx + dy * dy + dz * dz);
             const float x = dx * inv_len, y = dy * inv_len, z = dz * inv_len;

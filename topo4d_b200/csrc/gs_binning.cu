@@ -182,6 +182,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const GsParams
 }
 
 // ---- K4 ----
+#ifndef GS_SORT_UNROLL
+#define GS_SORT_UNROLL 1
+#endif
+constexpr int SORT_UNROLL = GS_SORT_UNROLL;     // instances in flight per thread in the gather epilogue
 constexpr int SORT_THREADS = 128;
 constexpr int SORT_REG_KEYS = 2048;    // lists up to here are sorted in registers (<= 16 keys per thread) ...
 constexpr int SORT_LONG_THREADS = 1024;
@@ -349,7 +353,9 @@ __global__ void __launch_bounds__(SORT_THREADS, 8) sort_gather_kernel(const GsPa
     __shared__ __align__(16) unsigned long long s_keys[SORT_REG_KEYS];
     __shared__ long long s_tile;
     const int tid = threadIdx.x;
-    // non-empty tiles come from the device-side queue the scan kernel filled (dynamic load balance)
+    // non-empty tiles come from the device-side queue the scan kernel filled (dynamic load balance; asking for the next tile ahead of
+    // time was measured: it hides two L2 round trips per tile but hands the leftover tiles to the CTAs that hold the longest lists --
+    // 0.034 -> 0.044 ms at 3 views, nothing at 24)
     for (;;) {
         if (tid == 0) {
             s_tile = gs_active_tile(p, atomicAdd(&p.status->q_sort, 1u));
@@ -378,31 +384,22 @@ __global__ void __launch_bounds__(SORT_THREADS, 8) sort_gather_kernel(const GsPa
         float4* __restrict__ rec = p.sorted_rec + start * 3;
         const int tl = (int)(tg - (long long)v * p.tiles);
         const float tx0 = (float)((tl % p.tiles_x) * GS_TILE), ty0 = (float)((tl / p.tiles_x) * GS_TILE);
-        // one thread per instance: Gaussian index out, block-reach mask into bits 24..31 of the key's low word
-        // (indices are < 2^24, validated on the host)
-        #pragma unroll 2
+        // one thread per instance: the three 16-byte parts of its record are requested together (ONE L2 round trip per instance, and
+        // two instances in flight per thread), then the exact block-reach mask, then the record leaves -- conic pre-scaled for the blend
+        // kernels (-A/2, -B, -C/2: exact), reach mask in bits 24..31 of the index word (indices are < 2^24, validated on the host)
+        #pragma unroll SORT_UNROLL
         for (int k = tid; k < n; k += SORT_THREADS) {
-            const unsigned long long key = sorted[k];
-            const uint32_t id = (uint32_t)key & 0x00ffffffu;
+            const uint32_t id = (uint32_t)sorted[k] & 0x00ffffffu;
+            const float4* __restrict__ gr = geom + (size_t)id * 3;
+            float4 g0 = __ldg(gr), g1 = __ldg(gr + 1), g2 = __ldg(gr + 2);
             p.sorted_ids[start + k] = id;
-            const unsigned mask = block_reach_mask(__ldg(geom + (size_t)id * 3), __ldg(geom + (size_t)id * 3 + 1), tx0, ty0);
-            sorted[k] = key | ((unsigned long long)mask << 24);
-        }
-        __syncthreads();
-        // gather: 3 x 16 bytes per record, coalesced writes
-        #pragma unroll 4
-        for (int t = tid; t < n * 3; t += SORT_THREADS) {
-            const int k = t / 3, part = t - k * 3;
-            const uint32_t low = (uint32_t)sorted[k];
-            float4 val = __ldg(geom + (size_t)(low & 0x00ffffffu) * 3 + part);
+            const unsigned mask = block_reach_mask(g0, g1, tx0, ty0);
 #if GS_PRESCALE
-            if (part == 0) { val.z *= -0.5f; val.w = -val.w; }     // conic pre-scaled for the blend kernels: -A/2, -B (exact)
-            else if (part == 1) val.x *= -0.5f;                    // -C/2
-            else val.w = __uint_as_float(low);                     // id | reach mask << 24
-#else
-            if (part == 2) val.w = __uint_as_float(low);
+            g0.z *= -0.5f; g0.w = -g0.w; g1.x *= -0.5f;
 #endif
-            rec[t] = val;
+            g2.w = __uint_as_float(id | (mask << 24));
+            float4* __restrict__ o = rec + (size_t)k * 3;
+            o[0] = g0; o[1] = g1; o[2] = g2;
         }
         __syncthreads();   // s_keys is reused by the next tile
     }
@@ -450,26 +447,19 @@ __global__ void __launch_bounds__(SORT_LONG_THREADS, 1) sort_gather_long_kernel(
         float4* __restrict__ rec = p.sorted_rec + start * 3;
         const int tl = (int)(tg - (long long)v * p.tiles);
         const float tx0 = (float)((tl % p.tiles_x) * GS_TILE), ty0 = (float)((tl / p.tiles_x) * GS_TILE);
-        for (int k = tid; k < n; k += SORT_LONG_THREADS) {
-            const unsigned long long key = s_long[k];
-            const uint32_t id = (uint32_t)key & 0x00ffffffu;
+        #pragma unroll 2
+        for (int k = tid; k < n; k += SORT_LONG_THREADS) {          // as in sort_gather_kernel: record in, reach mask, record out
+            const uint32_t id = (uint32_t)s_long[k] & 0x00ffffffu;
+            const float4* __restrict__ gr = geom + (size_t)id * 3;
+            float4 g0 = __ldg(gr), g1 = __ldg(gr + 1), g2 = __ldg(gr + 2);
             p.sorted_ids[start + k] = id;
-            const unsigned mask = block_reach_mask(__ldg(geom + (size_t)id * 3), __ldg(geom + (size_t)id * 3 + 1), tx0, ty0);
-            s_long[k] = key | ((unsigned long long)mask << 24);
-        }
-        __syncthreads();
-        for (int t = tid; t < n * 3; t += SORT_LONG_THREADS) {
-            const int k = t / 3, part = t - k * 3;
-            const uint32_t low = (uint32_t)s_long[k];
-            float4 val = __ldg(geom + (size_t)(low & 0x00ffffffu) * 3 + part);
+            const unsigned mask = block_reach_mask(g0, g1, tx0, ty0);
 #if GS_PRESCALE
-            if (part == 0) { val.z *= -0.5f; val.w = -val.w; }     // conic pre-scaled for the blend kernels: -A/2, -B (exact)
-            else if (part == 1) val.x *= -0.5f;                    // -C/2
-            else val.w = __uint_as_float(low);                     // id | reach mask << 24
-#else
-            if (part == 2) val.w = __uint_as_float(low);
+            g0.z *= -0.5f; g0.w = -g0.w; g1.x *= -0.5f;
 #endif
-            rec[t] = val;
+            g2.w = __uint_as_float(id | (mask << 24));
+            float4* __restrict__ o = rec + (size_t)k * 3;
+            o[0] = g0; o[1] = g1; o[2] = g2;
         }
         __syncthreads();
     }

@@ -107,14 +107,6 @@ __device__ __forceinline__ float splat_exp(float power)
     float y = __fmul_rn(power, LOG2E), g;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(y));
     return g;
-#elif GS_EXP_MODE == 3
-    // mode 2 without the log2(e) tail term: |power| <= 5.6 on the blend path, so dropping power * 1.9e-8 costs <= 1.1e-7 relative (one more ulp)
-    const float L2E_HI = 1.4426950216293335f, LN2 = 0.6931471805599453f;
-    const float y = __fmul_rn(power, L2E_HI);
-    const float r = __fmaf_rn(power, L2E_HI, -y);
-    float g;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(y));
-    return __fmaf_rn(g, __fmul_rn(r, LN2), g);
 #else
     const float L2E_HI = 1.4426950216293335f, L2E_LO = 1.9259629911266175e-8f, LN2 = 0.6931471805599453f;
     const float y = __fmul_rn(power, L2E_HI);

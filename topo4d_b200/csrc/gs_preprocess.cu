@@ -45,7 +45,10 @@ __device__ __forceinline__ Rect tile_rect(float pix_x, float pix_y, float radius
 // and every per-Gaussian input -- the 12 16-byte SH loads included -- is requested at the top, before the projection and
 // covariance arithmetic that used to sit between a thread's loads, so ~20 loads per thread are in flight at once.  Registers
 // (up to 128 at 128-thread CTAs) are cheaper here than exposed L2 round trips.  Results are unchanged (same operations, same order).
-__global__ void __launch_bounds__(128, 4) preprocess_kernel(const GsParams p, int32_t* __restrict__ radii)
+#ifndef GS_PRE_MINB
+#define GS_PRE_MINB 6
+#endif
+__global__ void __launch_bounds__(128, GS_PRE_MINB) preprocess_kernel(const GsParams p, int32_t* __restrict__ radii)
 {
     __shared__ float s_cam[2][GS_CAM_FLOATS];
     __shared__ __align__(16) float s_sh[4][32 * SH_ROW];
