@@ -136,14 +136,20 @@ __device__ __forceinline__ bool clear_of_border(int xmin, int xmax, int ymin, in
 template <int STAGE>
 __global__ void __launch_bounds__(256)
 f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ triangles, int nver, int ntri, int h, int w,
-               int y_lo, int y_hi, const int* __restrict__ nonflat, unsigned* __restrict__ dmax, unsigned* __restrict__ imax)
+               int y_lo, int y_hi, const int* __restrict__ nonflat, unsigned* __restrict__ dmax, unsigned* __restrict__ imax, int split_log2)
 {
     const bool flat = *nonflat == 0;
     if (STAGE == 0 && flat) return;
     const int lane = threadIdx.x & 31;
+    // 2^split_log2 warps share a group of 32 triangles: all of them load the group (one triangle per lane), each walks the boxes whose
+    // lane index is congruent to its part.  With one warp per group a 120 k-triangle bake was a single wave of 3 752 warps, each walking
+    // its 32 boxes (~1 100 pixels each) one after the other on its own dependent-latency clock: 0.38 ms at an IPC of 0.4, and as long
+    // as the slowest warp (the rows of triangles along the image border take the general test).  The host picks the split from the
+    // mean box size; meshes of pixel-sized triangles (one lane per box, 32 boxes per warp at once) keep one warp per group.
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long base = warp_global * 32; base < ntri; base += nwarps * 32) {
+    const int split = 1 << split_log2, part = (int)(warp_global & (split - 1));
+    const long long ngroups = (((long long)gridDim.x * blockDim.x) >> 5) >> split_log2;
+    for (long long base = (warp_global >> split_log2) * 32; base < ntri; base += ngroups * 32) {
         const int i = (int)(base + lane);
         Tri t;
         bool ok = false;
@@ -151,7 +157,7 @@ f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ trian
         int bw = 0, area = 0;
         if (ok) { bw = t.xmax - t.xmin + 1; const long long a = (long long)bw * (t.ymax - t.ymin + 1); area = a > 0x7fffffffLL ? 0x7fffffff : (int)a; }
         const bool fast = STAGE == 1 && flat && ok && clear_of_border(t.xmin, t.xmax, t.ymin, t.ymax, h, w);
-        if (ok && area <= SMALL_BOX) {
+        if (ok && area <= SMALL_BOX && (lane & (split - 1)) == part) {
             const TriSetup ts = tri_setup(t);
             if (fast) {
                 for (int x = t.xmin; x <= t.xmax; x++) {
@@ -165,7 +171,7 @@ f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ trian
                     for (int x = t.xmin; x <= t.xmax; x++) test_pixel<STAGE>(t, ts, i, x, y, h, w, y_lo, flat, dmax, imax);
             }
         }
-        unsigned big = __ballot_sync(0xffffffffu, ok && area > SMALL_BOX);
+        unsigned big = __ballot_sync(0xffffffffu, ok && area > SMALL_BOX && (lane & (split - 1)) == part);
         const unsigned big_fast = __ballot_sync(0xffffffffu, fast);
         while (big) {
             const int src = __ffs(big) - 1;
@@ -180,13 +186,20 @@ f3d_tri_kernel(const float* __restrict__ vertices, const int* __restrict__ trian
             const int sidx = (int)base + src;
             const TriSetup ts = tri_setup(s);                  // once per triangle (every lane computes the same values)
             if (STAGE == 1 && ((big_fast >> src) & 1u)) {
-                // the warp covers the box in steps of (32 / cw) rows x cw columns, cw = the box width rounded up to a power of two (<= 32):
-                // a lane keeps its column -- the column products are computed once per 32-column block -- and walks down the rows
-                const int sh = sbw > 16 ? 5 : sbw > 8 ? 4 : sbw > 4 ? 3 : sbw > 2 ? 2 : 1;
-                const int col = lane & ((1 << sh) - 1), rof = lane >> sh, rstep = 32 >> sh;
+                // the warp covers the box in steps of (32 / cw) rows x cw columns and moves right by cw columns per block; a lane keeps its
+                // column -- the column products are computed once per block -- and walks down the rows.  cw = the power of two in 8..32
+                // that wastes the fewest lanes on the last block (a 34-pixel box: 8 -> 85 % of the lanes busy, 32 -> 53 %), boxes
+                // narrower than 8 take the next power of two
+                int sh;
+                if (sbw <= 8) sh = sbw > 4 ? 3 : sbw > 2 ? 2 : 1;
+                else {
+                    const int w32 = ((sbw + 31) & ~31) - sbw, w16 = ((sbw + 15) & ~15) - sbw, w8 = ((sbw + 7) & ~7) - sbw;
+                    sh = (w32 <= w16 && w32 <= w8) ? 5 : (w16 <= w8 ? 4 : 3);
+                }
+                const int cw = 1 << sh, col = lane & (cw - 1), rof = lane >> sh, rstep = 32 >> sh;
                 const int symax = s.ymin + sarea / sbw - 1;
                 const unsigned key = 0xffffffffu - (unsigned)sidx;
-                for (int x0 = col; x0 < sbw; x0 += 32) {
+                for (int x0 = col; x0 < sbw; x0 += cw) {
                     const int x = s.xmin + x0;
                     const float v2x = (float)x - s.x0;
                     const float ax = ts.v0x * v2x, bx = ts.v1x * v2x;
@@ -506,7 +519,11 @@ static int f3d_run(float* image, uint8_t* image_u8, bool fill, const float* vert
     if (cudaMemsetAsync(nonflat, 0, 256, s) != cudaSuccess) return F3D_E_CUDA;
     if (nver > 0) f3d_flat_kernel<<<sms * 2, 256, 0, s>>>(vertices, nver, nonflat);
     if (rec) f3d_setup_kernel<<<(ntri + 255) / 256, 256, 0, s>>>(vertices, triangles, colors, nver, ntri, rec);
-    const long long warps_needed = ((long long)ntri + 31) / 32;
+    // warps per group of 32 triangles: 8 when a triangle covers hundreds of pixels (the 8K bake of a 120 k-triangle head: ~560), 1 for
+    // pixel-sized triangles (measured at 9.6 M triangles: 1.46 ms with 1, 1.95 / 2.86 / 4.30 ms with 2 / 4 / 8)
+    const long long px_per_tri = ntri > 0 ? (long long)h * w / ntri : 0;
+    const int split_log2 = px_per_tri >= 256 ? 3 : px_per_tri >= 96 ? 2 : px_per_tri >= 48 ? 1 : 0;
+    const long long warps_needed = (((long long)ntri + 31) / 32) << split_log2;
     long long blocks1 = (warps_needed + 7) / 8;
     if (blocks1 > (long long)sms * 64) blocks1 = (long long)sms * 64;
     if (blocks1 < 1) blocks1 = 1;
@@ -515,8 +532,8 @@ static int f3d_run(float* image, uint8_t* image_u8, bool fill, const float* vert
         if (cudaMemsetAsync(imax, 0, (size_t)band * w * sizeof(unsigned), s) != cudaSuccess) return F3D_E_CUDA;
         f3d_clear_if_nonflat_kernel<<<sms * 4, 256, 0, s>>>(dmax, (size_t)band * w, nonflat);      // the depth plane only when it will be used
         if (ntri > 0) {
-            f3d_tri_kernel<0><<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, y_lo, y_hi, nonflat, dmax, imax);
-            f3d_tri_kernel<1><<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, y_lo, y_hi, nonflat, dmax, imax);
+            f3d_tri_kernel<0><<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, y_lo, y_hi, nonflat, dmax, imax, split_log2);
+            f3d_tri_kernel<1><<<(unsigned)blocks1, 256, 0, s>>>(vertices, triangles, nver, ntri, h, w, y_lo, y_hi, nonflat, dmax, imax, split_log2);
         }
         const dim3 grid2((unsigned)((w + 255) / 256), (unsigned)(rows < 65535 ? rows : 65535));
         const bool vec4 = rec && (w & 3) == 0 && (((uintptr_t)image | (uintptr_t)image_u8 | (uintptr_t)imax) & 15u) == 0;
