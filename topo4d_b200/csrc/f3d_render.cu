@@ -113,6 +113,9 @@ __device__ __forceinline__ void test_pixel(const Tri& t, const TriSetup& ts, int
     else if (flat || dmax[pix] == orderable(d)) atomicMax(imax + pix, 0xffffffffu - (unsigned)idx);
 }
 
+#ifndef F3D_SPLIT_MAX_LOG2
+#define F3D_SPLIT_MAX_LOG2 4
+#endif
 constexpr int SMALL_BOX = 48;   // bbox pixels a single lane walks by itself
 
 // The texture bake's case -- every vertex z is 0 and the bbox keeps clear of the 2-pixel image border -- needs no depth and no border
@@ -318,77 +321,100 @@ f3d_shade_rec_kernel(float* __restrict__ image, uint8_t* __restrict__ image_u8, 
 // The same resolve with FOUR consecutive pixels of a row per thread (w % 4 == 0, 16-byte aligned planes): one 16-byte key load, the
 // triangle record is fetched once per run of equal winners (inside a triangle all four pixels share it), and the twelve colour values
 // leave as three 16-byte stores (fp32) or three 4-byte stores (uint8) instead of twelve scalar ones.  Same per-pixel arithmetic.
+struct RecCache { int idx; float4 q0, q1, q2, q3, q4, q5; };
+
+template <bool FILL, bool U8>
+__device__ __forceinline__ void shade4_row(float* __restrict__ image, uint8_t* __restrict__ image_u8, const float4* __restrict__ rec,
+                                           float* __restrict__ depth, float depth_init, int ntri, int w, int x4, int y, const uint4 k4, RecCache& rc)
+{
+    int& cached = rc.idx;
+    float4 &q0 = rc.q0, &q1 = rc.q1, &q2 = rc.q2, &q3 = rc.q3, &q4 = rc.q4, &q5 = rc.q5;
+    const size_t pix = (size_t)y * w + x4;
+    const unsigned key[4] = {k4.x, k4.y, k4.z, k4.w};
+    float col[12];
+    bool drawn[4];
+    #pragma unroll
+    for (int e = 0; e < 4; e++) {
+        drawn[e] = false;
+        col[3 * e] = col[3 * e + 1] = col[3 * e + 2] = 0.f;
+        if (key[e] == 0u) continue;
+        const int idx = (int)(0xffffffffu - key[e]);
+        if (idx < 0 || idx >= ntri) continue;
+        if (idx != cached) {
+            const float4* __restrict__ r = rec + (size_t)idx * F3D_REC_F4;
+            q0 = __ldg(r); q1 = __ldg(r + 1); q2 = __ldg(r + 2); q3 = __ldg(r + 3); q4 = __ldg(r + 4); q5 = __ldg(r + 5);
+            cached = idx;
+        }
+        Tri t;
+        t.x0 = q0.x; t.y0 = q0.y; t.z0 = q2.z; t.z1 = q2.w; t.z2 = q3.x;
+        TriSetup s;
+        s.v0x = q0.z; s.v0y = q0.w; s.v1x = q1.x; s.v1y = q1.y; s.dot00 = q1.z; s.dot01 = q1.w; s.dot11 = q2.x; s.inv = q2.y;
+        float w0, w1, w2; bool inside;
+        bary_px((float)(x4 + e), (float)y, t, s, w0, w1, w2, inside);
+        const float d = w0 * t.z0 + w1 * t.z1 + w2 * t.z2;
+        drawn[e] = d > (depth ? depth[pix + e] : depth_init);
+        if (drawn[e]) {
+            if (depth) depth[pix + e] = d;
+            col[3 * e] = w0 * q3.y + w1 * q4.x + w2 * q4.w;
+            col[3 * e + 1] = w0 * q3.z + w1 * q4.y + w2 * q5.x;
+            col[3 * e + 2] = w0 * q3.w + w1 * q4.z + w2 * q5.y;
+        }
+    }
+    if (FILL || (drawn[0] && drawn[1] && drawn[2] && drawn[3])) {
+        if (U8) {
+            unsigned b[3];
+            #pragma unroll
+            for (int q = 0; q < 3; q++)
+                b[q] = (unsigned)(unsigned char)(int)(col[4 * q] * 255.0f) | ((unsigned)(unsigned char)(int)(col[4 * q + 1] * 255.0f) << 8) |
+                       ((unsigned)(unsigned char)(int)(col[4 * q + 2] * 255.0f) << 16) | ((unsigned)(unsigned char)(int)(col[4 * q + 3] * 255.0f) << 24);
+            unsigned* __restrict__ o = reinterpret_cast<unsigned*>(image_u8 + pix * 3);
+            o[0] = b[0]; o[1] = b[1]; o[2] = b[2];
+        } else {
+            float4* __restrict__ o = reinterpret_cast<float4*>(image + pix * 3);
+            o[0] = make_float4(col[0], col[1], col[2], col[3]);
+            o[1] = make_float4(col[4], col[5], col[6], col[7]);
+            o[2] = make_float4(col[8], col[9], col[10], col[11]);
+        }
+    } else {
+        #pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (!drawn[e]) continue;
+            if (U8) {
+                uint8_t* __restrict__ o = image_u8 + (pix + e) * 3;
+                o[0] = (unsigned char)(int)(col[3 * e] * 255.0f); o[1] = (unsigned char)(int)(col[3 * e + 1] * 255.0f);
+                o[2] = (unsigned char)(int)(col[3 * e + 2] * 255.0f);
+            } else {
+                float* __restrict__ o = image + (pix + e) * 3;
+                o[0] = col[3 * e]; o[1] = col[3 * e + 1]; o[2] = col[3 * e + 2];
+            }
+        }
+    }
+}
+
+// F3D_SHADE_ROWS rows per trip: all their 16-byte key loads are requested before any row is shaded (the key is the first link of a
+// key -> record -> store chain of DRAM / L2 round trips), and the record fetched for one row usually serves the next.
+#ifndef F3D_SHADE_ROWS
+#define F3D_SHADE_ROWS 2
+#endif
 template <bool FILL, bool U8>
 __global__ void __launch_bounds__(256)
 f3d_shade_rec4_kernel(float* __restrict__ image, uint8_t* __restrict__ image_u8, const float4* __restrict__ rec, float* __restrict__ depth,
                       float depth_init, int ntri, int h, int w, int y_lo, int y_hi, const unsigned* __restrict__ imax)
 {
+    constexpr int R = F3D_SHADE_ROWS;
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x4 >= w) return;
-    for (int y = y_lo + blockIdx.y; y <= y_hi; y += gridDim.y) {
-        const size_t pix = (size_t)y * w + x4;
-        const uint4 k4 = *reinterpret_cast<const uint4*>(imax + (size_t)(y - y_lo) * w + x4);
-        const unsigned key[4] = {k4.x, k4.y, k4.z, k4.w};
-        float col[12];
-        bool drawn[4];
-        int cached = -1;
-        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0, q4 = q0, q5 = q0;
+    RecCache rc;
+    rc.idx = -1;
+    rc.q0 = rc.q1 = rc.q2 = rc.q3 = rc.q4 = rc.q5 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = y_lo + R * blockIdx.y; y <= y_hi; y += R * gridDim.y) {
+        const uint4* __restrict__ kp = reinterpret_cast<const uint4*>(imax + (size_t)(y - y_lo) * w + x4);
+        uint4 k[R];
         #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            drawn[e] = false;
-            col[3 * e] = col[3 * e + 1] = col[3 * e + 2] = 0.f;
-            if (key[e] == 0u) continue;
-            const int idx = (int)(0xffffffffu - key[e]);
-            if (idx < 0 || idx >= ntri) continue;
-            if (idx != cached) {
-                const float4* __restrict__ r = rec + (size_t)idx * F3D_REC_F4;
-                q0 = __ldg(r); q1 = __ldg(r + 1); q2 = __ldg(r + 2); q3 = __ldg(r + 3); q4 = __ldg(r + 4); q5 = __ldg(r + 5);
-                cached = idx;
-            }
-            Tri t;
-            t.x0 = q0.x; t.y0 = q0.y; t.z0 = q2.z; t.z1 = q2.w; t.z2 = q3.x;
-            TriSetup s;
-            s.v0x = q0.z; s.v0y = q0.w; s.v1x = q1.x; s.v1y = q1.y; s.dot00 = q1.z; s.dot01 = q1.w; s.dot11 = q2.x; s.inv = q2.y;
-            float w0, w1, w2; bool inside;
-            bary_px((float)(x4 + e), (float)y, t, s, w0, w1, w2, inside);
-            const float d = w0 * t.z0 + w1 * t.z1 + w2 * t.z2;
-            drawn[e] = d > (depth ? depth[pix + e] : depth_init);
-            if (drawn[e]) {
-                if (depth) depth[pix + e] = d;
-                col[3 * e] = w0 * q3.y + w1 * q4.x + w2 * q4.w;
-                col[3 * e + 1] = w0 * q3.z + w1 * q4.y + w2 * q5.x;
-                col[3 * e + 2] = w0 * q3.w + w1 * q4.z + w2 * q5.y;
-            }
-        }
-        if (FILL || (drawn[0] && drawn[1] && drawn[2] && drawn[3])) {
-            if (U8) {
-                unsigned b[3];
-                #pragma unroll
-                for (int q = 0; q < 3; q++)
-                    b[q] = (unsigned)(unsigned char)(int)(col[4 * q] * 255.0f) | ((unsigned)(unsigned char)(int)(col[4 * q + 1] * 255.0f) << 8) |
-                           ((unsigned)(unsigned char)(int)(col[4 * q + 2] * 255.0f) << 16) | ((unsigned)(unsigned char)(int)(col[4 * q + 3] * 255.0f) << 24);
-                unsigned* __restrict__ o = reinterpret_cast<unsigned*>(image_u8 + pix * 3);
-                o[0] = b[0]; o[1] = b[1]; o[2] = b[2];
-            } else {
-                float4* __restrict__ o = reinterpret_cast<float4*>(image + pix * 3);
-                o[0] = make_float4(col[0], col[1], col[2], col[3]);
-                o[1] = make_float4(col[4], col[5], col[6], col[7]);
-                o[2] = make_float4(col[8], col[9], col[10], col[11]);
-            }
-        } else {
-            #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                if (!drawn[e]) continue;
-                if (U8) {
-                    uint8_t* __restrict__ o = image_u8 + (pix + e) * 3;
-                    o[0] = (unsigned char)(int)(col[3 * e] * 255.0f); o[1] = (unsigned char)(int)(col[3 * e + 1] * 255.0f);
-                    o[2] = (unsigned char)(int)(col[3 * e + 2] * 255.0f);
-                } else {
-                    float* __restrict__ o = image + (pix + e) * 3;
-                    o[0] = col[3 * e]; o[1] = col[3 * e + 1]; o[2] = col[3 * e + 2];
-                }
-            }
-        }
+        for (int r = 0; r < R; r++) k[r] = y + r <= y_hi ? kp[(size_t)r * (w / 4)] : make_uint4(0u, 0u, 0u, 0u);
+        #pragma unroll
+        for (int r = 0; r < R; r++)
+            if (y + r <= y_hi) shade4_row<FILL, U8>(image, image_u8, rec, depth, depth_init, ntri, w, x4, y + r, k[r], rc);
     }
 }
 
@@ -519,14 +545,18 @@ static int f3d_run(float* image, uint8_t* image_u8, bool fill, const float* vert
     if (cudaMemsetAsync(nonflat, 0, 256, s) != cudaSuccess) return F3D_E_CUDA;
     if (nver > 0) f3d_flat_kernel<<<sms * 2, 256, 0, s>>>(vertices, nver, nonflat);
     if (rec) f3d_setup_kernel<<<(ntri + 255) / 256, 256, 0, s>>>(vertices, triangles, colors, nver, ntri, rec);
-    // warps per group of 32 triangles: 8 when a triangle covers hundreds of pixels (the 8K bake of a 120 k-triangle head: ~560), 1 for
+    // warps per group of 32 triangles: 16 when a triangle covers hundreds of pixels (the 8K bake of a 120 k-triangle head: ~560), 1 for
     // pixel-sized triangles (measured at 9.6 M triangles: 1.46 ms with 1, 1.95 / 2.86 / 4.30 ms with 2 / 4 / 8)
     const long long px_per_tri = ntri > 0 ? (long long)h * w / ntri : 0;
-    const int split_log2 = px_per_tri >= 256 ? 3 : px_per_tri >= 96 ? 2 : px_per_tri >= 48 ? 1 : 0;
+    const int split_log2 = px_per_tri >= 256 ? F3D_SPLIT_MAX_LOG2 : px_per_tri >= 96 ? 2 : px_per_tri >= 48 ? 1 : 0;
     const long long warps_needed = (((long long)ntri + 31) / 32) << split_log2;
     long long blocks1 = (warps_needed + 7) / 8;
     if (blocks1 > (long long)sms * 64) blocks1 = (long long)sms * 64;
     if (blocks1 < 1) blocks1 = 1;
+    {   // a group's warps are consecutive global warp indices: the grid must hold whole groups (8 warps per block)
+        const long long m = (1ll << split_log2) > 8 ? (1ll << split_log2) / 8 : 1;
+        blocks1 = (blocks1 + m - 1) / m * m;
+    }
     for (int y_lo = 0; y_lo < h; y_lo += band) {
         const int y_hi = (y_lo + band < h ? y_lo + band : h) - 1, rows = y_hi - y_lo + 1;
         if (cudaMemsetAsync(imax, 0, (size_t)band * w * sizeof(unsigned), s) != cudaSuccess) return F3D_E_CUDA;
@@ -538,7 +568,7 @@ static int f3d_run(float* image, uint8_t* image_u8, bool fill, const float* vert
         const dim3 grid2((unsigned)((w + 255) / 256), (unsigned)(rows < 65535 ? rows : 65535));
         const bool vec4 = rec && (w & 3) == 0 && (((uintptr_t)image | (uintptr_t)image_u8 | (uintptr_t)imax) & 15u) == 0;
         if (vec4) {
-            const dim3 grid4((unsigned)((w / 4 + 255) / 256), grid2.y);
+            const dim3 grid4((unsigned)((w / 4 + 255) / 256), (unsigned)((rows + F3D_SHADE_ROWS - 1) / F3D_SHADE_ROWS < 65535 ? (rows + F3D_SHADE_ROWS - 1) / F3D_SHADE_ROWS : 65535));
             if (fill && image_u8) f3d_shade_rec4_kernel<true, true><<<grid4, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
             else if (fill) f3d_shade_rec4_kernel<true, false><<<grid4, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
             else if (image_u8) f3d_shade_rec4_kernel<false, true><<<grid4, 256, 0, s>>>(image, image_u8, rec, depth_buffer, depth_init, ntri, h, w, y_lo, y_hi, imax);
