@@ -168,7 +168,7 @@ int gs_mark_visible(int32_t N, const float* means3D, const float* camera, uint8_
 typedef struct GsWorkspaceView {
     const uint32_t* tile_start;     /* [V*tiles+1] exclusive scan: tile t of view v owns [start[v*tiles+t], start[..+1]) */
     const uint32_t* sorted_ids;     /* [cap] Gaussian index per instance, tile-major, (depth, index) ascending */
-    const float*    sorted_records; /* [cap,12] 48-byte records (x,y,conA,conB | conC,opacity,depth,thr | r,g,b,id) */
+    const float*    sorted_records; /* [cap,12] 48-byte records (x,y,-conA/2,-conB | -conC/2,opacity,depth,thr | r,g,b,id + reach mask << 24) */
     const float*    geom_records;   /* [V*N,12] same layout, per (view, Gaussian) */
     const float*    final_T;        /* [V,H,W] */
     const uint32_t* n_contrib;      /* [V,H,W] */

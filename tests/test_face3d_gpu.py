@@ -24,7 +24,11 @@ def test_golden_fixtures_bit_exact():
         np.testing.assert_array_equal(img, g[n + "_image"], err_msg=n)
 
 
-@pytest.mark.parametrize("grid,res,zmode", [(31, 256, "flat"), (64, 512, "random"), (300, 1024, "flat"), (7, 333, "random")])
+# the last six cases walk the stage-1 warp split (16 / 4 / 2 warps per group of 32 triangles, chosen from the mean box size), groups that
+# are not full, the flat fast path next to the general one, and widths that are not a multiple of four (scalar shade pass)
+@pytest.mark.parametrize("grid,res,zmode", [(31, 256, "flat"), (64, 512, "random"), (300, 1024, "flat"), (7, 333, "random"),
+                                            (9, 256, "flat"), (12, 256, "flat"), (20, 256, "random"), (20, 258, "flat"),
+                                            (1, 100, "flat"), (5, 1001, "flat")])
 def test_matches_reference_cpu(grid, res, zmode):
     v, t, c = synth.uv_grid_mesh(grid=grid, res=res, seed=grid)
     if zmode == "random":
@@ -88,16 +92,17 @@ def test_full_size_properties_8k():
     assert float((img.sum(-1) != 0).float().mean()) > 0.95
 
 
+@pytest.mark.parametrize("grid,res", [(40, 300), (12, 256), (9, 514)])
 @pytest.mark.parametrize("zmode", ["flat", "random"])
-def test_fused_bake_path_float_and_u8(zmode):
+def test_fused_bake_path_float_and_u8(zmode, grid=40, res=300):
     """render_colors without BG takes the fused bake (f3d_bake_colors: fresh image, private constant depth, optional uint8):
     bit-identical to the reference followed by (image * 255).astype(uint8), for all-zero z (one key stage) and general z (two)."""
-    v, t, c = synth.uv_grid_mesh(grid=40, res=300, seed=7)
+    v, t, c = synth.uv_grid_mesh(grid=grid, res=res, seed=7)
     if zmode == "random":
         v[:, 2] = np.random.default_rng(3).normal(size=v.shape[0])
-    ref, _ = _cpu(v, t, c, 300, 300, 3)
-    np.testing.assert_array_equal(f3d_render.render_colors(v, t, c, 300, 300, 3), ref)
-    np.testing.assert_array_equal(f3d_render.render_colors_u8(v, t, c, 300, 300, 3), (ref * 255).astype(np.uint8))
+    ref, _ = _cpu(v, t, c, res, res, 3)
+    np.testing.assert_array_equal(f3d_render.render_colors(v, t, c, res, res, 3), ref)
+    np.testing.assert_array_equal(f3d_render.render_colors_u8(v, t, c, res, res, 3), (ref * 255).astype(np.uint8))
     # an empty mesh still yields the zero image (render.py:66)
     assert not f3d_render.render_colors(v, t[:0], c, 64, 48, 3).any()
 

@@ -53,9 +53,10 @@ constexpr int WPC = GS_WPC;
 // ffs -> address -> LDS -> FMA chain, so the kernels want warps more than registers (measured at 64-thread CTAs:
 // bwd 12 -> 72 regs, fwd 14 -> 70 regs, no spills, 5-8 % faster than the unconstrained build).
 // One worker in GS_FILL_EVERY starts on the background-fill queue (the others start blending); a few warps are enough
-// to keep the HBM write stream busy, the rest hide the blend path's latency.
+// to keep the HBM write stream busy, the rest hide the blend path's latency.  Re-measured with the r02q kernels (blend_fwd, 24 views):
+// 3 -> 0.543 ms, 4 -> 0.500, 5 -> 0.476, 6 -> 0.470, 8 -> 0.480, 12 -> 0.557.
 #ifndef GS_FILL_EVERY
-#define GS_FILL_EVERY 8
+#define GS_FILL_EVERY 6
 #endif
 #ifndef GS_BWD_MINB
 #define GS_BWD_MINB (24 / GS_WPC)
