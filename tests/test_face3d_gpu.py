@@ -94,7 +94,7 @@ def test_full_size_properties_8k():
 
 @pytest.mark.parametrize("grid,res", [(40, 300), (12, 256), (9, 514)])
 @pytest.mark.parametrize("zmode", ["flat", "random"])
-def test_fused_bake_path_float_and_u8(zmode, grid=40, res=300):
+def test_fused_bake_path_float_and_u8(zmode, grid, res):
     """render_colors without BG takes the fused bake (f3d_bake_colors: fresh image, private constant depth, optional uint8):
     bit-identical to the reference followed by (image * 255).astype(uint8), for all-zero z (one key stage) and general z (two)."""
     v, t, c = synth.uv_grid_mesh(grid=grid, res=res, seed=7)
