@@ -643,9 +643,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 constexpr int QROW = 8;                       // floats per parked quad row (per part)
 constexpr int QW_OFF = 8 * QROW + 16;         // second part (colour / depth moments) starts 16 banks away from the first
 
-// 7 CTAs x 4 warps per SM (<= 73 registers, no spills): measured 0.789 ms vs 0.807 (6 CTAs, 80 registers) / 0.800 (8 CTAs, 64 + stack)
+// Minimum-CTAs hint 6 (<= 80 registers allowed): ptxas still allocates 72 registers, so 7 CTAs x 4 warps stay resident per SM, but it
+// schedules the record loop differently from the hint-7 build -- measured with the r02r kernel 0.745 ms vs 0.752 (hint 7) vs 0.770
+// (hint 5).  (r02e, older kernel: 0.789 ms at hint 7 vs 0.807 at 6 / 0.800 at 8 with 64 registers + stack.)
 #ifndef GS_BWDM_MINB
-#define GS_BWDM_MINB (28 / GS_WPC)
+#define GS_BWDM_MINB (24 / GS_WPC)
 #endif
 __global__ void __launch_bounds__(WPC * 32, GS_BWDM_MINB)
 blend_bwd_mma_kernel(const GsParams p, const GsBackwardIO io)
