@@ -1,6 +1,7 @@
 // gs_api.cu -- C-ABI entry points of the Gaussian rasterizer (declared in include/topo4d_b200.h).
 // Host-side sequencing only: validates arguments, carves the caller's workspace, enqueues kernels.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "gs_common.cuh"
 
@@ -15,6 +16,16 @@ static int record_cuda(cudaError_t e, const char* what)
 #define CK(call) do { int _r = record_cuda((call), #call); if (_r) return _r; } while (0)
 #define CK_LAUNCH(name) do { int _r = record_cuda(cudaGetLastError(), name); if (_r) return _r; \
     if (p->debug) { _r = record_cuda(cudaStreamSynchronize(s), name " (debug sync)"); if (_r) return _r; } } while (0)
+
+int gs_pdl_enabled()
+{
+    static int cached = -1;                      // benign race: every thread computes the same value
+    if (cached < 0) {
+        const char* e = getenv("TOPO4D_B200_PDL");
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached;
+}
 
 static int sm_count()
 {

@@ -63,6 +63,7 @@ template <int K, int LPG>   // K = (deg+1)^2 active SH coefficients, 0 = colors_
 __global__ void __launch_bounds__(128, 3)
 preprocess_bwd_kernel(const GsParams p, const GsBackwardIO io)
 {
+    gs_pdl_wait();                                           // launched as a dependent of the blend backward (grad2d)
     const int t_global = blockIdx.x * blockDim.x + threadIdx.x;
     const int i_raw = t_global / LPG, vq = t_global % LPG;  // Gaussian, view sub-lane (LPG lanes share a Gaussian's views: 4, or 1 when V <= 2)
     const bool act = i_raw < p.N;                            // inactive lanes still take part in the shuffles
@@ -320,12 +321,12 @@ template <int LPG>
 static void launch_pbwd(const GsParams& p, const GsBackwardIO& io, cudaStream_t s)
 {
     const int threads = 128, blocks = (int)(((long long)p.N * LPG + threads - 1) / threads);
-    if (!p.shs) { preprocess_bwd_kernel<0, LPG><<<blocks, threads, 0, s>>>(p, io); return; }
+    if (!p.shs) { gs_launch_dependent(preprocess_bwd_kernel<0, LPG>, dim3(blocks), dim3(threads), 0, s, p, io); return; }
     switch (p.deg) {
-        case 0: preprocess_bwd_kernel<1, LPG><<<blocks, threads, 0, s>>>(p, io); break;
-        case 1: preprocess_bwd_kernel<4, LPG><<<blocks, threads, 0, s>>>(p, io); break;
-        case 2: preprocess_bwd_kernel<9, LPG><<<blocks, threads, 0, s>>>(p, io); break;
-        default: preprocess_bwd_kernel<16, LPG><<<blocks, threads, 0, s>>>(p, io); break;
+        case 0: gs_launch_dependent(preprocess_bwd_kernel<1, LPG>, dim3(blocks), dim3(threads), 0, s, p, io); break;
+        case 1: gs_launch_dependent(preprocess_bwd_kernel<4, LPG>, dim3(blocks), dim3(threads), 0, s, p, io); break;
+        case 2: gs_launch_dependent(preprocess_bwd_kernel<9, LPG>, dim3(blocks), dim3(threads), 0, s, p, io); break;
+        default: gs_launch_dependent(preprocess_bwd_kernel<16, LPG>, dim3(blocks), dim3(threads), 0, s, p, io); break;
     }
 }
 

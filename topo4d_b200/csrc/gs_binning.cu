@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const GsParams
     __shared__ uint32_t s_warp[32];
     __shared__ unsigned long long s_prefix;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    gs_pdl_trigger();                                   // scatter_kernel may become resident now (it waits for this grid's completion)
     if (FUSED) {
         __shared__ uint32_t s_sum[32];
         __shared__ uint32_t s_max[32];
@@ -353,6 +354,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 8) sort_gather_kernel(const GsPa
     __shared__ __align__(16) unsigned long long s_keys[SORT_REG_KEYS];
     __shared__ long long s_tile;
     const int tid = threadIdx.x;
+    gs_pdl_wait();
+    gs_pdl_trigger();
     // non-empty tiles come from the device-side queue the scan kernel filled (dynamic load balance; asking for the next tile ahead of
     // time was measured: it hides two L2 round trips per tile but hands the leftover tiles to the CTAs that hold the longest lists --
     // 0.034 -> 0.044 ms at 3 views, nothing at 24)
@@ -415,6 +418,8 @@ __global__ void __launch_bounds__(SORT_LONG_THREADS, 1) sort_gather_long_kernel(
     extern __shared__ __align__(16) unsigned long long s_long[];
     __shared__ long long s_tile;
     const int tid = threadIdx.x;
+    gs_pdl_wait();
+    gs_pdl_trigger();
     for (;;) {
         if (tid == 0) {
             const unsigned q = atomicAdd(&p.status->q_sort_long, 1u);
@@ -502,11 +507,11 @@ void gs_launch_sort_gather(const GsParams& p, int num_sms, cudaStream_t s)
             cudaFuncSetAttribute((const void*)sort_gather_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_LONG_KEYS * 8);
             attr_set = true;
         }
-        sort_gather_long_kernel<<<num_sms, SORT_LONG_THREADS, SORT_LONG_KEYS * 8, s>>>(p);
+        gs_launch_dependent(sort_gather_long_kernel, dim3(num_sms), dim3(SORT_LONG_THREADS), SORT_LONG_KEYS * 8, s, p);
     }
     long long blocks = p.total_tiles;
     const long long maxb = (long long)num_sms * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    sort_gather_kernel<<<(unsigned)blocks, SORT_THREADS, 0, s>>>(p);
+    gs_launch_dependent(sort_gather_kernel, dim3((unsigned)blocks), dim3(SORT_THREADS), 0, s, p);
 }

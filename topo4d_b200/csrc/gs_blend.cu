@@ -250,6 +250,7 @@ blend_fwd_kernel(const GsParams p, float* __restrict__ out_color, float* __restr
     float4 (*const ring)[CHUNK * 3] = s_rec[warp];
     uint64_t* const bar = s_bar[warp];
     constexpr unsigned ALL = (1u << PX) - 1u;
+    gs_pdl_wait();                                              // launched as a dependent of sort_gather_kernel
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
     __syncwarp();
     uint32_t phases = 0u;                       // bit b = parity to wait for on bar[b]
@@ -409,6 +410,7 @@ blend_bwd_kernel(const GsParams p, const GsBackwardIO io)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 (*const ring)[CHUNK * 3] = s_rec[warp];
     uint64_t* const bar = s_bar[warp];
+    gs_pdl_trigger();                                           // preprocess_bwd_kernel may become resident (it waits for this grid)
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
     __syncwarp();
     uint32_t phases = 0u;
@@ -660,6 +662,7 @@ blend_bwd_mma_kernel(const GsParams p, const GsBackwardIO io)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 (*const ring)[CHUNK * 3] = s_rec[warp];
     uint64_t* const bar = s_bar[warp];
+    gs_pdl_trigger();                                           // preprocess_bwd_kernel may become resident (it waits for this grid)
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
     __syncwarp();
     uint32_t phases = 0u;
@@ -868,7 +871,7 @@ static void launch_fwd(const GsParams& p, float* color, float* depth, float* alp
 {
     static thread_local int grid = 0, grid_sms = 0;
     if (grid == 0 || grid_sms != num_sms) { grid = resident_ctas((const void*)blend_fwd_kernel<PX>, WPC * 32, num_sms, 4); grid_sms = num_sms; }
-    blend_fwd_kernel<PX><<<grid, WPC * 32, 0, s>>>(p, color, depth, alpha);
+    gs_launch_dependent(blend_fwd_kernel<PX>, dim3(grid), dim3(WPC * 32), 0, s, p, color, depth, alpha);
 }
 template <int PX>
 static void launch_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms, cudaStream_t s)

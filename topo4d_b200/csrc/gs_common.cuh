@@ -136,6 +136,28 @@ void gs_launch_blend_bwd(const GsParams& p, const GsBackwardIO& io, int num_sms,
 void gs_launch_preprocess_bwd(const GsParams& p, const GsBackwardIO& io, cudaStream_t s);
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (sm_90+) ----
+// The seven kernels of a step depend on each other in stream order, and between two dependent launches the GPU idles for the 2-4 us it
+// takes to drain one grid and bring up the next: nothing for a 24-view step, 10 % of the reference's one-view step.  A kernel launched
+// through gs_launch_dependent may become resident while its predecessor still runs -- as soon as every CTA of the predecessor has
+// executed gs_pdl_trigger() -- and parks at gs_pdl_wait(), its first statement, until the predecessor grid has completed and its memory
+// operations are visible (which transitively covers everything earlier in the stream).  TOPO4D_B200_PDL=0 restores plain launches.
+int gs_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gs_launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = gs_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void gs_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gs_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // i-th work item of the non-empty-tile queue (long tiles first), or -1 past the end
 __device__ __forceinline__ long long gs_active_tile(const GsParams& p, unsigned i)
 {

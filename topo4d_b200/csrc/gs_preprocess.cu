@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(128, GS_PRE_MINB) preprocess_kernel(const GsPa
 // (atomic cursor); the per-tile sort restores (depth, id) order, a total order on distinct keys.
 __global__ void __launch_bounds__(256) scatter_kernel(const GsParams p, const int32_t* __restrict__ radii)
 {
+    gs_pdl_wait();                                                                // tile_start comes from the scan kernel
+    gs_pdl_trigger();
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;                  // V * N < 2^31 (validated on the host)
     if (gid >= (unsigned)p.V * (unsigned)p.N) return;
     const int rad = radii[gid];
@@ -295,7 +297,7 @@ void gs_launch_scatter(const GsParams& p, const int32_t* radii, cudaStream_t s)
 {
     const long long n = (long long)p.V * p.N;
     if (n == 0) return;
-    scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, radii);
+    gs_launch_dependent(scatter_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p, radii);
 }
 
 void gs_launch_mark_visible(int N, const float* means3D, const float* cam, uint8_t* visible, cudaStream_t s)
