@@ -135,7 +135,7 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp"
 
     def __init__(self, index):
         self.rows, self.proc, self.t0, self.t1 = [], None, None, None
@@ -148,8 +148,16 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        # every row is stamped with nvidia-smi's OWN sample time (last field): the pipe may deliver rows late and in bursts
+        import datetime
         for ln in self.proc.stdout:
-            self.rows.append((time.time(), ln.strip()))
+            ln = ln.strip()
+            stamp = time.time()
+            try:
+                stamp = datetime.datetime.strptime(ln.rsplit(",", 1)[1].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:  # noqa: BLE001  (unexpected format: fall back to the arrival time)
+                pass
+            self.rows.append((stamp, ln))
 
     def mark(self, which):
         setattr(self, which, time.time())
@@ -159,7 +167,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e18)] or [r for _, r in self.rows]
+        # samples inside the timed region; the region (tens of ms) is often shorter than the 50 ms sampling period, so the
+        # window is widened by one period on each side, and failing that the three samples nearest to it are taken -- never the
+        # idle-time samples from before the warm-up (the sampler starts early, see run_ours)
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else 1e18
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for t, r in self.rows if t0 - 0.06 <= t <= t1 + 0.06]
+        if not rows:
+            mid = 0.5 * (t0 + min(t1, t0 + 3600.0))
+            rows = [r for _, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
         sm, mx, reasons = [], [], set()
         for r in rows:
             f = [x.strip() for x in r.split(",")]
@@ -400,6 +416,9 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # the clock sampler (nvidia-smi -lms 50) is started HERE, seconds before the timed region: its process start-up and driver
+    # attach would otherwise land inside a 30 ms timed region (observed once: a 1.68 ms/step outlier among runs at 1.59)
+    sampler = ClockSampler(local) if rank == 0 else None
     scene, cams = workload(a)
     my_views = parallel.shard_views(a.views, rank, world)
     H, W = a.height, a.width
@@ -469,7 +488,6 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(a.warmup, 3)):
         step(t)
     barrier()
