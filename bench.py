@@ -162,6 +162,17 @@ class ClockSampler:
     def mark(self, which):
         setattr(self, which, time.time())
 
+    @staticmethod
+    def select_rows(rows, t0, t1):
+        """rows: [(sample time, csv line)].  Lines sampled inside [t0, t1], else within one sampling period of it, else the three nearest."""
+        t0 = t0 if t0 is not None else 0.0
+        t1 = t1 if t1 is not None else 1e18
+        sel = [r for t, r in rows if t0 <= t <= t1] or [r for t, r in rows if t0 - 0.06 <= t <= t1 + 0.06]
+        if not sel:
+            mid = 0.5 * (t0 + min(t1, t0 + 3600.0))
+            sel = [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+        return sel
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -170,12 +181,7 @@ class ClockSampler:
         # samples inside the timed region; the region (tens of ms) is often shorter than the 50 ms sampling period, so the
         # window is widened by one period on each side, and failing that the three samples nearest to it are taken -- never the
         # idle-time samples from before the warm-up (the sampler starts early, see run_ours)
-        t0 = self.t0 if self.t0 is not None else 0.0
-        t1 = self.t1 if self.t1 is not None else 1e18
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for t, r in self.rows if t0 - 0.06 <= t <= t1 + 0.06]
-        if not rows:
-            mid = 0.5 * (t0 + min(t1, t0 + 3600.0))
-            rows = [r for _, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+        rows = self.select_rows(self.rows, self.t0, self.t1)
         sm, mx, reasons = [], [], set()
         for r in rows:
             f = [x.strip() for x in r.split(",")]
