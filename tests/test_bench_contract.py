@@ -47,5 +47,5 @@ def test_clock_sampler_picks_the_samples_of_the_timed_region():
     rows = [(100.00, "idle-a"), (100.05, "idle-b"), (103.00, "warm"), (103.05, "load-1"), (103.10, "load-2"), (105.0, "e2e")]
     assert bench.ClockSampler.select_rows(rows, 103.04, 103.11) == ["load-1", "load-2"]
     assert bench.ClockSampler.select_rows(rows, 103.06, 103.09) == ["warm", "load-1", "load-2"]  # region shorter than the period: +- one period
-    assert bench.ClockSampler.select_rows(rows, 104.0, 104.01) == ["e2e", "load-2", "load-1"]   # nothing near: the three nearest, never the idle rows
+    assert sorted(bench.ClockSampler.select_rows(rows, 104.0, 104.01)) == ["e2e", "load-1", "load-2"]   # nothing near: the three nearest, never the idle rows
     assert bench.ClockSampler.select_rows([], 1.0, 2.0) == []
